@@ -1,0 +1,64 @@
+"""Shared helpers for the parity tests (mirrors the helpers at the bottom of the reference's
+tests/detector.rs:296-435)."""
+import os
+import wave
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def golden(name: str) -> str:
+    return os.path.join(GOLDEN, name)
+
+
+def read_wav_i16(path: str) -> np.ndarray:
+    with wave.open(path) as w:
+        assert w.getsampwidth() == 2 and w.getnchannels() == 1 and w.getframerate() == 16000
+        return np.frombuffer(w.readframes(w.getnframes()), dtype="<i2").copy()
+
+
+def read_wav_buffer(path: str, gain: float) -> bytes:
+    """tests/detector.rs:405-426 — strips a 44-byte header and applies an i16 gain."""
+    raw = open(path, "rb").read()[44:]
+    raw = raw[: len(raw) // 2 * 2]
+    s = np.frombuffer(raw, dtype="<i2").astype(np.float32) * np.float32(gain)
+    # f32::round = half away from zero
+    r = np.where(s >= 0, np.floor(s + np.float32(0.5)), np.ceil(s - np.float32(0.5)))
+    return np.clip(r, -32768, 32767).astype("<i2").tobytes()
+
+
+def two_wakeword_stream(gain1: float = 1.0, gain2: float = 1.0) -> bytes:
+    """tests/detector.rs:372-400: 5 s silence + sample 1 + 5 s + sample 2 + 5 s, 16 kHz i16 LE."""
+    sil = bytes(16000 * 2 * 5)
+    return sil + read_wav_buffer(golden("oye_casa_g_1.wav"), gain1) + sil + read_wav_buffer(golden("oye_casa_g_2.wav"), gain2) + sil
+
+
+def run_detection_simulation(detector, stream: bytes):
+    """tests/detector.rs:355-363: feed get_bytes_per_frame() chunks, collect detections."""
+    n = detector.get_bytes_per_frame()
+    out = []
+    for off in range(0, len(stream) - n + 1, n):
+        d = detector.process_bytes(stream[off : off + n])
+        if d is not None:
+            out.append(d)
+    return out
+
+
+def synth_audio(n_streams: int, n_samples: int, seed: int = 0x5EED) -> np.ndarray:
+    """SURVEY §8d synthetic audio: 0.1*N(0,1) noise + a per-stream chirp 200->3000 Hz at 0.3,
+    clipped to [-1,1]; never exactly zero."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n_samples, dtype=np.float64) / 16000.0
+    dur = n_samples / 16000.0
+    out = np.empty((n_streams, n_samples), np.float32)
+    for b in range(n_streams):
+        noise = 0.1 * rng.standard_normal(n_samples)
+        f0 = 200.0 + 37.0 * (b % 13)
+        k = (3000.0 - f0) / max(dur, 1e-9)
+        chirp = 0.3 * np.sin(2 * np.pi * (f0 * t + 0.5 * k * t * t) + 0.1 * b)
+        x = np.clip(noise + chirp, -1.0, 1.0).astype(np.float32)
+        x[x == 0] = np.float32(1e-4)
+        out[b] = x
+    return out
