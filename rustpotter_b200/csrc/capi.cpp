@@ -1,0 +1,553 @@
+// extern "C" surface declared in include/rustpotter_b200.h.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <optional>
+
+#include "audio_frontend.h"
+#include "detector_core.h"
+#include "engine.h"
+#include "kernels.h"
+#include "mfcc_tables.h"
+#include "rp_internal.h"
+#include "stream_state.h"
+
+using namespace rp;
+
+namespace {
+constexpr uint32_t kMagicHandle = 0x52504831;  // "RPH1"
+constexpr uint32_t kMagicBatch = 0x52504231;   // "RPB1"
+struct HandleBase {
+    uint32_t magic;
+    std::string error;
+};
+int g_dtw_variant = 0;
+}  // namespace
+
+struct rp_handle {
+    HandleBase base{kMagicHandle, {}};
+    std::unique_ptr<DetectorCore> core;
+    AudioIngest ingest;
+    std::optional<GainNormalizer> gain_filter;
+    std::optional<BandPass> band_pass;
+    float rms_level = 0.f, gain = 1.f;
+    std::vector<Emitted> emitted;
+    std::vector<float> score_store;
+    mutable std::vector<float> partial_store;
+};
+
+struct rp_batch {
+    HandleBase base{kMagicBatch, {}};
+    std::unique_ptr<DetectorCore> core;
+    std::vector<Emitted> emitted;
+    std::vector<rp_batch_detection> dets;
+    std::vector<std::vector<float>> stores;
+};
+
+namespace {
+
+template <typename H, typename F>
+int guarded(H* h, F&& f) {
+    try {
+        return f();
+    } catch (const Error& e) {
+        if (h) h->base.error = e.what();
+        set_thread_error(e.what());
+        return e.code;
+    } catch (const std::exception& e) {
+        if (h) h->base.error = e.what();
+        set_thread_error(e.what());
+        return RP_ERR_INVALID;
+    }
+}
+
+void make_filters(rp_handle* h, const rp_config& c) {
+    h->gain_filter.reset();
+    h->band_pass.reset();
+    if (c.gain_normalizer_enabled)
+        h->gain_filter.emplace(c.min_gain, c.max_gain, c.gain_ref_set ? std::optional<float>(c.gain_ref) : std::nullopt);
+    if (c.band_pass_enabled) h->band_pass.emplace((float)kSampleRate, c.low_cutoff, c.high_cutoff);
+}
+
+void after_wakeword_change(rp_handle* h) {  // detector.rs:336-338
+    const WakewordSet& ws = h->core->wakewords();
+    if (h->gain_filter) h->gain_filter->set_rms_level_ref(ws.target_rms_level, (size_t)(ws.max_frames / 3));
+}
+
+// Rustpotter::process_audio (detector.rs:347-376)
+int process_audio(rp_handle* h, std::vector<float> audio, rp_detection* out) {
+    if (h->core->wakewords().empty()) return 0;
+    h->rms_level = GainNormalizer::rms_level(audio);
+    if (h->gain_filter) h->gain = h->gain_filter->filter(audio, h->rms_level);
+    if (h->band_pass) h->band_pass->filter(audio);
+    h->core->process(audio.data(), (int64_t)audio.size(), false, &h->gain, h->emitted);
+    if (h->emitted.empty()) return 0;
+    if (out) h->core->fill_detection(h->emitted.front().det, out, h->score_store);
+    return 1;
+}
+
+template <typename T>
+int process_samples(rp_handle* h, const T* samples, size_t n, float max_value, rp_detection* out) {
+    if (!h) return RP_ERR_INVALID;
+    return guarded(h, [&] {
+        if (!samples || n != h->ingest.input_samples_per_frame) return 0;  // detector.rs:249-251
+        return process_audio(h, h->ingest.convert(samples, n, max_value), out);
+    });
+}
+
+// device-resident MFCC tables for the raw kernel entry point, one per (device, mfcc_size)
+struct TableCache {
+    DeviceBuffer hamming, tw, mel, centres, dct;
+    MfccTablesDev dev;
+};
+std::mutex g_table_mutex;
+std::map<std::pair<int, int>, std::unique_ptr<TableCache>> g_tables;
+
+const MfccTablesDev& tables_for(int device, int mfcc_size, cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(g_table_mutex);
+    auto key = std::make_pair(device, mfcc_size);
+    auto it = g_tables.find(key);
+    if (it != g_tables.end()) return it->second->dev;
+    MfccTables t = build_mfcc_tables(mfcc_size);
+    auto c = std::make_unique<TableCache>();
+    auto up = [&](DeviceBuffer& b, const void* p, size_t bytes) {
+        b.reserve(bytes, "mfcc tables");
+        cuda_check(cudaMemcpyAsync(b.as<void>(), p, bytes, cudaMemcpyHostToDevice, s), "mfcc tables");
+    };
+    up(c->hamming, t.hamming.data(), t.hamming.size() * 4);
+    up(c->tw, t.tw480.data(), t.tw480.size() * 4);
+    up(c->mel, t.mel_bank.data(), t.mel_bank.size() * 4);
+    up(c->centres, t.centres.data(), t.centres.size() * 4);
+    up(c->dct, t.dct.data(), t.dct.size() * 4);
+    cuda_check(cudaStreamSynchronize(s), "mfcc tables");
+    c->dev.hamming = c->hamming.as<float>();
+    c->dev.tw480 = c->tw.as<float2>();
+    c->dev.mel_bank = c->mel.as<float>();
+    c->dev.centres = c->centres.as<int>();
+    c->dev.dct = c->dct.as<float>();
+    c->dev.num_coefficients = t.num_coefficients;
+    auto& ref = *c;
+    g_tables[key] = std::move(c);
+    return ref.dev;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rp_version(void) { return "rustpotter-b200 0.1.0 (path of rustpotter 3.0.2)"; }
+
+int rp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void rp_config_default(rp_config* c) {  // src/config.rs:20-29,43-52,63-71,193-208
+    if (!c) return;
+    std::memset(c, 0, sizeof(*c));
+    c->sample_rate = 16000;
+    c->sample_format = RP_FMT_F32;
+    c->channels = 1;
+    c->endianness = RP_ENDIAN_LITTLE;
+    c->avg_threshold = 0.2f;
+    c->threshold = 0.5f;
+    c->min_scores = 5;
+    c->eager = 0;
+    c->score_ref = 0.22f;
+    c->band_size = 5;
+    c->score_mode = RP_SCORE_MAX;
+    c->vad_mode = RP_VAD_NONE;
+    c->gain_normalizer_enabled = 0;
+    c->gain_ref_set = 0;
+    c->gain_ref = 0.f;
+    c->min_gain = 0.1f;
+    c->max_gain = 1.0f;
+    c->band_pass_enabled = 0;
+    c->low_cutoff = 80.f;
+    c->high_cutoff = 400.f;
+}
+
+const char* rp_last_error(const void* handle_or_null) {
+    if (!handle_or_null) return thread_error();
+    const HandleBase* b = static_cast<const HandleBase*>(handle_or_null);
+    if (b->magic != kMagicHandle && b->magic != kMagicBatch) return "invalid handle";
+    return b->error.c_str();
+}
+
+// ------------------------------------------------------------------ per-stream handle
+int rp_create(const rp_config* cfg, int device, rp_handle** out) {
+    if (!cfg || !out) return RP_ERR_INVALID;
+    *out = nullptr;
+    return guarded((rp_handle*)nullptr, [&] {
+        auto h = std::make_unique<rp_handle>();
+        h->core = std::make_unique<DetectorCore>(*cfg, 1, device);
+        h->ingest.fmt = cfg->sample_format;
+        h->ingest.channels = cfg->channels;
+        h->ingest.endianness = cfg->endianness;
+        h->ingest.input_samples_per_frame = (size_t)(cfg->sample_rate * 30 / 1000) * cfg->channels;
+        make_filters(h.get(), *cfg);
+        *out = h.release();
+        return RP_OK;
+    });
+}
+
+void rp_destroy(rp_handle* h) { delete h; }
+
+int rp_add_wakeword_from_buffer(rp_handle* h, const char* key, const uint8_t* buf, size_t len) {
+    if (!h || !key || !buf) return RP_ERR_INVALID;
+    return guarded(h, [&] {
+        h->core->add_wakeword(key, buf, len);
+        after_wakeword_change(h);
+        return RP_OK;
+    });
+}
+
+int rp_add_wakeword_from_file(rp_handle* h, const char* key, const char* path) {
+    if (!h || !key || !path) return RP_ERR_INVALID;
+    return guarded(h, [&] {
+        std::vector<uint8_t> b = read_file(path);
+        h->core->add_wakeword(key, b.data(), b.size());
+        after_wakeword_change(h);
+        return RP_OK;
+    });
+}
+
+int rp_remove_wakeword(rp_handle* h, const char* key) {
+    if (!h || !key) return RP_ERR_INVALID;
+    return guarded(h, [&] {
+        if (!h->core->remove_wakeword(key)) return 0;
+        after_wakeword_change(h);
+        return 1;
+    });
+}
+
+int rp_remove_wakewords(rp_handle* h) {
+    if (!h) return RP_ERR_INVALID;
+    return guarded(h, [&] {
+        if (!h->core->remove_wakewords()) return 0;
+        after_wakeword_change(h);
+        return 1;
+    });
+}
+
+size_t rp_get_samples_per_frame(const rp_handle* h) { return h ? h->ingest.input_samples_per_frame : 0; }
+size_t rp_get_bytes_per_frame(const rp_handle* h) { return h ? h->ingest.input_bytes_per_frame() : 0; }
+
+int rp_get_partial_detection(const rp_handle* h, rp_detection* out) {
+    if (!h) return RP_ERR_INVALID;
+    const auto& p = h->core->partial(0);
+    if (!p) return 0;
+    if (out) h->core->fill_detection(*p, out, h->partial_store);
+    return 1;
+}
+
+float rp_get_rms_level(const rp_handle* h) { return h ? h->rms_level : 0.f; }
+float rp_get_gain(const rp_handle* h) { return h ? h->gain : 1.f; }
+float rp_get_rms_level_ref(const rp_handle* h) {
+    return h && h->gain_filter ? h->gain_filter->rms_level_ref : std::numeric_limits<float>::quiet_NaN();
+}
+
+int rp_process_bytes(rp_handle* h, const uint8_t* bytes, size_t len, rp_detection* out) {
+    if (!h) return RP_ERR_INVALID;
+    return guarded(h, [&] {
+        if (!bytes || len != h->ingest.input_bytes_per_frame()) return 0;  // detector.rs:235-237
+        return process_audio(h, h->ingest.decode_bytes(bytes, len), out);
+    });
+}
+int rp_process_samples_i8(rp_handle* h, const int8_t* s, size_t n, rp_detection* out) { return process_samples(h, s, n, 127.f, out); }
+int rp_process_samples_i16(rp_handle* h, const int16_t* s, size_t n, rp_detection* out) { return process_samples(h, s, n, 32767.f, out); }
+int rp_process_samples_i32(rp_handle* h, const int32_t* s, size_t n, rp_detection* out) {
+    return process_samples(h, s, n, (float)2147483647, out);
+}
+int rp_process_samples_f32(rp_handle* h, const float* s, size_t n, rp_detection* out) { return process_samples(h, s, n, 0.f, out); }
+
+int rp_update_detector_config(rp_handle* h, const rp_config* cfg) {
+    if (!h || !cfg) return RP_ERR_INVALID;
+    return guarded(h, [&] {
+        h->core->update_detector_config(*cfg);
+        return RP_OK;
+    });
+}
+int rp_update_filters_config(rp_handle* h, const rp_config* cfg) {
+    if (!h || !cfg) return RP_ERR_INVALID;
+    return guarded(h, [&] {
+        // detector.rs:283-289: fresh filters (the gain reference is NOT re-derived from the
+        // wakewords until the next wakeword change), then reset()
+        make_filters(h, *cfg);
+        h->core->reset();
+        return RP_OK;
+    });
+}
+int rp_update_config(rp_handle* h, const rp_config* cfg) {
+    int r = rp_update_detector_config(h, cfg);
+    return r != RP_OK ? r : rp_update_filters_config(h, cfg);
+}
+void rp_reset(rp_handle* h) {
+    if (h) h->core->reset();
+}
+uint64_t rp_windows_scored(const rp_handle* h) { return h ? h->core->windows_scored() : 0; }
+
+// ------------------------------------------------------------------ batch
+int rp_batch_create(const rp_config* cfg, int64_t n_streams, int device, rp_batch** out) {
+    if (!cfg || !out) return RP_ERR_INVALID;
+    *out = nullptr;
+    return guarded((rp_batch*)nullptr, [&] {
+        if (cfg->gain_normalizer_enabled || cfg->band_pass_enabled)
+            throw Error(RP_ERR_UNSUPPORTED, "audio filters are not available on the batched front-end yet");
+        auto b = std::make_unique<rp_batch>();
+        b->core = std::make_unique<DetectorCore>(*cfg, n_streams, device);
+        b->core->engine().set_dtw_variant(g_dtw_variant);
+        *out = b.release();
+        return RP_OK;
+    });
+}
+void rp_batch_destroy(rp_batch* b) { delete b; }
+
+int rp_batch_add_wakeword_from_buffer(rp_batch* b, const char* key, const uint8_t* buf, size_t len) {
+    if (!b || !key || !buf) return RP_ERR_INVALID;
+    return guarded(b, [&] {
+        b->core->add_wakeword(key, buf, len);
+        return RP_OK;
+    });
+}
+int rp_batch_add_wakeword_from_file(rp_batch* b, const char* key, const char* path) {
+    if (!b || !key || !path) return RP_ERR_INVALID;
+    return guarded(b, [&] {
+        std::vector<uint8_t> f = read_file(path);
+        b->core->add_wakeword(key, f.data(), f.size());
+        return RP_OK;
+    });
+}
+int rp_batch_remove_wakewords(rp_batch* b) {
+    if (!b) return RP_ERR_INVALID;
+    return guarded(b, [&] { return b->core->remove_wakewords() ? 1 : 0; });
+}
+int rp_batch_set_cuda_stream(rp_batch* b, void* s) {
+    if (!b) return RP_ERR_INVALID;
+    return guarded(b, [&] {
+        b->core->engine().set_cuda_stream(static_cast<cudaStream_t>(s));
+        return RP_OK;
+    });
+}
+int rp_batch_process(rp_batch* b, const float* audio, int64_t S, int on_device, const rp_batch_detection** dets, int64_t* n_dets) {
+    if (!b || !audio) return RP_ERR_INVALID;
+    return guarded(b, [&] {
+        b->core->engine().set_dtw_variant(g_dtw_variant);
+        b->core->process(audio, S, on_device != 0, nullptr, b->emitted);
+        b->dets.resize(b->emitted.size());
+        b->stores.resize(b->emitted.size());
+        for (size_t i = 0; i < b->emitted.size(); i++) {
+            b->dets[i].stream = b->emitted[i].stream;
+            b->dets[i].chunk = b->emitted[i].chunk;
+            b->core->fill_detection(b->emitted[i].det, &b->dets[i].det, b->stores[i]);
+        }
+        if (dets) *dets = b->dets.data();
+        if (n_dets) *n_dets = (int64_t)b->dets.size();
+        return RP_OK;
+    });
+}
+int rp_batch_update_config(rp_batch* b, const rp_config* cfg) {
+    if (!b || !cfg) return RP_ERR_INVALID;
+    return guarded(b, [&] {
+        b->core->update_detector_config(*cfg);
+        return RP_OK;
+    });
+}
+void rp_batch_reset(rp_batch* b) {
+    if (b) b->core->reset();
+}
+uint64_t rp_batch_windows_scored(const rp_batch* b) { return b ? b->core->windows_scored() : 0; }
+int64_t rp_batch_n_streams(const rp_batch* b) { return b ? b->core->engine().n_streams() : 0; }
+int rp_batch_max_mfcc_frames(const rp_batch* b) { return b ? b->core->wakewords().max_frames : 0; }
+int rp_batch_last_timings(const rp_batch* b, float* ms, int cap) {
+    if (!b || !ms) return 0;
+    int n = 0;
+    for (; n < 4 && n < cap; n++) ms[n] = b->core->engine().timings_ms[n];
+    if (n < cap) ms[n++] = b->core->host_ms;
+    return n;
+}
+int rp_batch_last_launches(const rp_batch* b) { return b ? b->core->engine().launches : 0; }
+
+// ------------------------------------------------------------------ raw kernels
+int rp_mfcc_frames(const float* audio_dev, int64_t n_streams, int64_t S, int mfcc_size, float* out_dev, void* cuda_stream) {
+    return guarded((rp_handle*)nullptr, [&] {
+        if (!audio_dev || !out_dev || n_streams < 1 || mfcc_size < 1 || mfcc_size > kMaxMfccSize) throw Error(RP_ERR_INVALID, "bad argument");
+        const int64_t hops = S / kHopSamples;
+        if (hops <= 3) return RP_OK;
+        int dev = 0;
+        cuda_check(cudaGetDevice(&dev), "cudaGetDevice");
+        cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+        const MfccTablesDev& t = tables_for(dev, mfcc_size, s);
+        // frame i <-> hop i+3, covering samples [160*(i+1), 160*(i+1)+480)  (extractor.rs:69-79)
+        cuda_check(launch_mfcc_frames(audio_dev, S, nullptr, n_streams, (int)(hops - 3), kHopSamples, t, out_dev, hops - 3, 0,
+                                      nullptr, s), "mfcc kernel");
+        return RP_OK;
+    });
+}
+
+int rp_dtw_scores(const float* tmpl_dev, const int64_t* tmpl_off_dev, const int32_t* tmpl_len_dev, int tmpl_len_uniform,
+                  const float* win_dev, const int64_t* win_off_dev, const int32_t* win_len_dev, int win_len_uniform,
+                  int64_t n_pairs, int d, int band, float score_ref, int cmn, float* out_dev, void* cuda_stream) {
+    return guarded((rp_handle*)nullptr, [&] {
+        if (!tmpl_dev || !win_dev || !out_dev || d < 1 || tmpl_len_uniform < 1 || win_len_uniform < 1 || band < 0)
+            throw Error(RP_ERR_INVALID, "bad argument");
+        DtwPairsArgs a;
+        a.tmpl = tmpl_dev;
+        a.tmpl_off = tmpl_off_dev;
+        a.tmpl_len = tmpl_len_dev;
+        a.tmpl_len_max = tmpl_len_uniform;
+        a.win = win_dev;
+        a.win_off = win_off_dev;
+        a.win_len = win_len_dev;
+        a.win_len_max = win_len_uniform;
+        a.n_pairs = n_pairs;
+        a.d = d;
+        a.band = band;
+        a.score_ref = score_ref;
+        a.cmn = cmn;
+        a.out = out_dev;
+        cuda_check(launch_dtw_pairs_generic(a, static_cast<cudaStream_t>(cuda_stream)), "dtw kernel");
+        return RP_OK;
+    });
+}
+
+int rp_set_dtw_variant(int v) {
+    g_dtw_variant = v;
+    return RP_OK;
+}
+
+// ------------------------------------------------------------------ host-logic hooks
+int rp_wakeword_inspect(const uint8_t* buf, size_t len, rp_wakeword_info* info) {
+    if (!buf || !info) return RP_ERR_INVALID;
+    return guarded((rp_handle*)nullptr, [&] {
+        WakewordRefData w = parse_rpw(buf, len);
+        std::memset(info, 0, sizeof(*info));
+        std::snprintf(info->name, RP_NAME_MAX, "%s", w.name.c_str());
+        info->mfcc_size = w.mfcc_size;
+        info->n_templates = (int)w.samples_features.size();
+        info->avg_frames = w.avg_features ? w.avg_features->rows : 0;
+        info->max_frames = w.max_frames();
+        info->has_threshold = w.threshold.has_value();
+        info->has_avg_threshold = w.avg_threshold.has_value();
+        info->threshold = w.threshold.value_or(0.f);
+        info->avg_threshold = w.avg_threshold.value_or(0.f);
+        info->rms_level = w.rms_level;
+        info->is_v2 = w.is_v2;
+        return RP_OK;
+    });
+}
+
+int rp_wakeword_template(const uint8_t* buf, size_t len, int t, char* name_out, float* out, size_t out_cap) {
+    if (!buf) return RP_ERR_INVALID;
+    return guarded((rp_handle*)nullptr, [&] {
+        WakewordRefData w = parse_rpw(buf, len);
+        const FrameMatrix* m = nullptr;
+        const char* nm = "";
+        if (t < 0) {
+            if (!w.avg_features) return 0;
+            m = &*w.avg_features;
+        } else {
+            if (t >= (int)w.samples_features.size()) throw Error(RP_ERR_INVALID, "template index out of range");
+            m = &w.samples_features[(size_t)t].second;
+            nm = w.samples_features[(size_t)t].first.c_str();
+        }
+        if (name_out) std::snprintf(name_out, RP_NAME_MAX, "%s", nm);
+        if (out) {
+            if (out_cap < m->v.size()) throw Error(RP_ERR_INVALID, "output buffer too small");
+            std::memcpy(out, m->v.data(), m->v.size() * sizeof(float));
+        }
+        return m->rows;
+    });
+}
+
+int rp_host_replay(const rp_config* cfg, const uint8_t* const* rpws, const size_t* rpw_lens, int n_rpw, const float* scores,
+                   int64_t n_frames, int n_slots, const float* vad_values, rp_batch_detection* out, int64_t out_cap,
+                   int64_t* n_out, uint64_t* windows_scored) {
+    if (!cfg || !rpws || !rpw_lens || !scores || !n_out) return RP_ERR_INVALID;
+    return guarded((rp_handle*)nullptr, [&] {
+        static thread_local WakewordSet ws;                       // keeps names alive for the caller
+        static thread_local std::vector<std::vector<float>> stores;
+        static thread_local std::vector<std::vector<const char*>> names;
+        ws = WakewordSet();
+        for (int i = 0; i < n_rpw; i++) ws.add("w" + std::to_string(i), parse_rpw(rpws[i], rpw_lens[i]));
+        ws.rebuild(*cfg);
+        if ((int)ws.slots.size() != n_slots) throw Error(RP_ERR_INVALID, "n_slots does not match the wakeword files");
+        names.clear();
+        for (auto& r : ws.refs) {
+            std::vector<const char*> n;
+            for (auto& t : r.samples_features) n.push_back(t.first.c_str());
+            names.push_back(std::move(n));
+        }
+        DetectorParams p;
+        p.max_frames = ws.max_frames;
+        p.min_scores = cfg->min_scores;
+        p.eager = cfg->eager != 0;
+        p.vad_mode = cfg->vad_mode;
+        StreamState st;
+        st.configure(p);
+        stores.clear();
+        int64_t n = 0;
+        const int64_t total_hops = n_frames + kHopsPerChunk;
+        std::vector<float> tmp((size_t)ws.max_templates);
+        for (int64_t c = 0; c * kHopsPerChunk < total_hops; c++) {
+            for (int k = 0; k < kHopsPerChunk; k++) {
+                const int64_t h = c * kHopsPerChunk + k;
+                if (h >= total_hops) break;
+                Hit hit;
+                const Hit* hp = nullptr;
+                float vv = 0.f;
+                if (h >= kHopsPerChunk) {
+                    const float* row = scores + (h - kHopsPerChunk) * (int64_t)n_slots;
+                    const Judgement jd = judge_window(row, ws.metas.data(), (int)ws.metas.size(), (int)cfg->score_mode);
+                    if (jd.wakeword >= 0) {
+                        const WakewordMeta& m = ws.metas[(size_t)jd.wakeword];
+                        hit.stream = 0;
+                        hit.frame = (int32_t)h;
+                        hit.wakeword = jd.wakeword;
+                        hit.avg_score = jd.avg_score;
+                        hit.score = jd.score;
+                        hit.scores = row + m.slot_begin + (m.has_avg ? 1 : 0);
+                        hit.n_scores = m.n_templates;
+                        hp = &hit;
+                    }
+                    if (vad_values) vv = vad_values[h - kHopsPerChunk];
+                }
+                PartialDetection det;
+                if (st.on_hop(p, hp, vv, 1.f, &det)) {
+                    if (out && n < out_cap) {
+                        stores.emplace_back(det.scores);
+                        rp_batch_detection& o = out[n];
+                        std::memset(&o, 0, sizeof(o));
+                        o.stream = 0;
+                        o.chunk = c;
+                        const WakewordRefData& r = ws.refs[(size_t)det.wakeword];
+                        std::snprintf(o.det.name, RP_NAME_MAX, "%s", r.name.c_str());
+                        o.det.avg_score = det.avg_score;
+                        o.det.score = det.score;
+                        o.det.counter = det.counter;
+                        o.det.gain = det.gain;
+                        o.det.n_scores = (uint32_t)det.scores.size();
+                        o.det.score_names = names[(size_t)det.wakeword].data();
+                    }
+                    n++;
+                    break;
+                }
+            }
+        }
+        // score_values pointers are taken after the loop: `stores` no longer reallocates
+        for (int64_t i = 0; out && i < std::min<int64_t>(n, out_cap); i++) out[i].det.score_values = stores[(size_t)i].data();
+        *n_out = n;
+        if (windows_scored) *windows_scored = st.windows_scored();
+        return RP_OK;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+#include "detector_core.h"
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+
+namespace rp {
+
+DetectorCore::DetectorCore(const rp_config& cfg, int64_t n_streams, int device) : cfg_(cfg) {
+    if (cfg.sample_rate != (uint32_t)kSampleRate)
+        throw Error(RP_ERR_UNSUPPORTED,
+                    "sample_rate != 16000 needs the reference's rubato resampler, which is outside this path");
+    if (cfg.sample_format > RP_FMT_F32 || cfg.channels == 0 || cfg.endianness > RP_ENDIAN_NATIVE || cfg.score_mode > RP_SCORE_P95 ||
+        cfg.vad_mode > RP_VAD_HARD)
+        throw Error(RP_ERR_INVALID, "invalid configuration value");
+    engine_ = std::make_unique<Engine>(device, n_streams);
+    states_.resize((size_t)n_streams);
+    params_.min_scores = cfg.min_scores;
+    params_.eager = cfg.eager != 0;
+    params_.vad_mode = cfg.vad_mode;
+    for (auto& s : states_) s.configure(params_);
+}
+
+void DetectorCore::add_wakeword(const std::string& key, const uint8_t* buf, size_t len) {
+    WakewordRefData ww = parse_rpw(buf, len);
+    const bool first = ws_.empty();
+    ws_.add(key, std::move(ww));  // throws RP_ERR_MISMATCH before touching anything
+    if (first) reset();           // detector.rs:305-307 (set_out_size happens in Engine::configure)
+    on_wakeword_change();
+}
+
+bool DetectorCore::remove_wakeword(const std::string& key) {
+    if (!ws_.remove(key)) return false;
+    on_wakeword_change();
+    return true;
+}
+
+bool DetectorCore::remove_wakewords() {
+    if (!ws_.clear()) return false;
+    on_wakeword_change();
+    return true;
+}
+
+void DetectorCore::on_wakeword_change() {
+    ws_.rebuild(cfg_);
+    params_.max_frames = ws_.max_frames;
+    engine_->configure(ws_, cfg_);
+    names_.clear();
+    for (auto& r : ws_.refs) {
+        std::vector<const char*> n;
+        for (auto& t : r.samples_features) n.push_back(t.first.c_str());
+        names_.push_back(std::move(n));
+    }
+    // Deviation: the reference would keep scoring a window longer than the new
+    // max_mfcc_frames after a removal; here the window is clamped to the new length.
+    for (auto& s : states_) s.clamp_window(params_.max_frames);
+}
+
+void DetectorCore::update_detector_config(const rp_config& cfg) {
+    cfg_.avg_threshold = cfg.avg_threshold;
+    cfg_.threshold = cfg.threshold;
+    cfg_.min_scores = cfg.min_scores;
+    cfg_.eager = cfg.eager;
+    cfg_.band_size = cfg.band_size;
+    cfg_.score_ref = cfg.score_ref;
+    cfg_.score_mode = cfg.score_mode;
+    cfg_.vad_mode = cfg.vad_mode;
+    params_.min_scores = cfg.min_scores;
+    params_.eager = cfg.eager != 0;
+    params_.vad_mode = cfg.vad_mode;
+    for (auto& s : states_) s.configure(params_);
+    ws_.rebuild(cfg_);
+    engine_->configure(ws_, cfg_);
+    reset();
+}
+
+void DetectorCore::reset() {
+    for (auto& s : states_) s.reset();
+}
+
+uint64_t DetectorCore::windows_scored() const {
+    uint64_t t = 0;
+    for (auto& s : states_) t += s.windows_scored();
+    return t;
+}
+
+void DetectorCore::process(const float* audio, int64_t S, bool on_device, const float* gains, std::vector<Emitted>& out) {
+    out.clear();
+    if (ws_.empty()) return;  // detector.rs:348-350: audio is dropped, extractor untouched
+    if (S <= 0 || S % kFrameSamples != 0) throw Error(RP_ERR_INVALID, "samples_per_stream must be a positive multiple of 480");
+    const bool vad = params_.vad_mode >= 0;
+    engine_->process(audio, S, on_device, vad, hits_, vad ? &vad_ : nullptr);
+
+    const auto t0 = std::chrono::steady_clock::now();
+    const int64_t n_chunks = S / kFrameSamples;
+    const int64_t n_hops = n_chunks * kHopsPerChunk;
+    const int64_t B = engine_->n_streams();
+    size_t hi = 0;
+    for (int64_t b = 0; b < B; b++) {
+        StreamState& st = states_[(size_t)b];
+        size_t h0 = hi;
+        while (hi < hits_.size() && hits_[hi].stream == b) hi++;
+        if (h0 == hi && st.idle() && !vad) {  // nothing can fire on this stream in this call
+            st.skip_hops(params_, n_hops);
+            continue;
+        }
+        size_t hp = h0;
+        for (int64_t c = 0; c < n_chunks;) {
+            if (st.idle() && !vad) {  // jump to the chunk that holds the next judged detection
+                while (hp < hi && hits_[hp].frame < c * kHopsPerChunk) hp++;
+                const int64_t next = hp < hi ? hits_[hp].frame / kHopsPerChunk : n_chunks;
+                if (next > c) {
+                    st.skip_hops(params_, (next - c) * kHopsPerChunk);
+                    c = next;
+                    continue;
+                }
+            }
+            const float gain = gains ? gains[c] : 1.f;
+            for (int k = 0; k < kHopsPerChunk; k++) {
+                const int64_t j = c * kHopsPerChunk + k;
+                while (hp < hi && hits_[hp].frame < j) hp++;
+                Hit hit;
+                const Hit* hptr = nullptr;
+                if (hp < hi && hits_[hp].frame == j) {
+                    const HitRecord& r = hits_[hp];
+                    hit.stream = b;
+                    hit.frame = r.frame;
+                    hit.wakeword = r.wakeword;
+                    hit.avg_score = r.avg_score;
+                    hit.score = r.score;
+                    hit.scores = r.scores;
+                    hit.n_scores = ws_.metas[(size_t)r.wakeword].n_templates;
+                    hptr = &hit;
+                }
+                PartialDetection det;
+                const float vv = vad ? vad_[(size_t)(b * n_hops + j)] : 0.f;
+                if (st.on_hop(params_, hptr, vv, gain, &det)) {
+                    out.push_back(Emitted{b, c, std::move(det)});
+                    break;  // find_map: the rest of this chunk's frames are dropped (detector.rs:372-375)
+                }
+            }
+            c++;
+        }
+    }
+    host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+void DetectorCore::fill_detection(const PartialDetection& d, rp_detection* out, std::vector<float>& score_store) const {
+    std::memset(out, 0, sizeof(*out));
+    const WakewordRefData& r = ws_.refs[(size_t)d.wakeword];
+    std::snprintf(out->name, RP_NAME_MAX, "%s", r.name.c_str());
+    out->avg_score = d.avg_score;
+    out->score = d.score;
+    out->counter = d.counter;
+    out->gain = d.gain;
+    score_store = d.scores;
+    out->n_scores = (uint32_t)score_store.size();
+    out->score_names = names_[(size_t)d.wakeword].data();
+    out->score_values = score_store.data();
+}
+
+}  // namespace rp

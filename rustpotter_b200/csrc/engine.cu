@@ -1,0 +1,284 @@
+#include "engine.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace rp {
+
+void cuda_check(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) throw Error(RP_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+DeviceBuffer::~DeviceBuffer() { release(); }
+void DeviceBuffer::release() {
+    if (p_) cudaFree(p_);
+    p_ = nullptr;
+    bytes_ = 0;
+}
+void DeviceBuffer::reserve(size_t bytes, const char* what) {
+    if (bytes <= bytes_) return;
+    release();
+    cuda_check(cudaMalloc(&p_, bytes), what);
+    bytes_ = bytes;
+}
+
+namespace {
+template <typename T>
+void upload(DeviceBuffer& buf, const std::vector<T>& v, cudaStream_t s, const char* what) {
+    buf.reserve(std::max<size_t>(v.size() * sizeof(T), 16), what);
+    if (!v.empty()) cuda_check(cudaMemcpyAsync(buf.as<void>(), v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s), what);
+}
+}  // namespace
+
+Engine::Engine(int device, int64_t n_streams) : device_(device), n_streams_(n_streams) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        throw Error(RP_ERR_CUDA, std::string("no usable CUDA device (this path has no CPU fallback): ") +
+                                     (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device < 0 || device >= count) throw Error(RP_ERR_INVALID, "device index out of range");
+    if (n_streams < 1) throw Error(RP_ERR_INVALID, "n_streams must be >= 1");
+    cuda_check(cudaSetDevice(device_), "cudaSetDevice");
+    cuda_check(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+    stream_ = own_stream_;
+    for (auto& ev : ev_) cuda_check(cudaEventCreate(&ev), "cudaEventCreate");
+    carry_.reserve((size_t)n_streams_ * 2 * kHopSamples * sizeof(float), "carry");
+    cuda_check(cudaMemsetAsync(carry_.as<void>(), 0, carry_.bytes(), stream_), "memset carry");
+    hit_count_.reserve(sizeof(int), "hit counter");
+    cuda_check(cudaMallocHost(&count_host_, sizeof(int)), "cudaMallocHost");
+}
+
+Engine::~Engine() {
+    cudaSetDevice(device_);
+    if (own_stream_) cudaStreamSynchronize(own_stream_);
+    for (auto& ev : ev_)
+        if (ev) cudaEventDestroy(ev);
+    if (hit_host_) cudaFreeHost(hit_host_);
+    if (count_host_) cudaFreeHost(count_host_);
+    if (own_stream_) cudaStreamDestroy(own_stream_);
+}
+
+void Engine::set_cuda_stream(cudaStream_t s) {
+    cuda_check(cudaSetDevice(device_), "cudaSetDevice");
+    cuda_check(cudaStreamSynchronize(stream_), "sync");
+    stream_ = s ? s : own_stream_;
+}
+
+const float* Engine::last_frames_dev(int64_t* rows_per_stream, int* first_new_row) const {
+    // process() flips cur_ after moving the history, so the last call wrote frames_[1 - cur_]
+    if (rows_per_stream) *rows_per_stream = hist_ + frames_cap_;
+    if (first_new_row) *first_new_row = hist_;
+    return frames_[1 - cur_].as<float>();
+}
+
+void Engine::configure(const WakewordSet& ws, const rp_config& cfg) {
+    cuda_check(cudaSetDevice(device_), "cudaSetDevice");
+    cuda_check(cudaStreamSynchronize(stream_), "sync");
+    band_ = (int)cfg.band_size;
+    score_ref_ = cfg.score_ref;
+    score_mode_ = (int)cfg.score_mode;
+    n_wakewords_ = (int)ws.refs.size();
+    n_slots_ = (int)ws.slots.size();
+    max_templates_ = ws.max_templates;
+    const int old_d = d_, old_hist = hist_;
+    d_ = ws.mfcc_size;
+    max_frames_ = ws.max_frames;
+    if (n_slots_ == 0) return;
+
+    // templates, packed in slot order
+    std::vector<float> tmpl;
+    std::vector<int64_t> off;
+    std::vector<int32_t> len;
+    max_slot_len_ = 0;
+    for (int s = 0; s < n_slots_; s++) {
+        const FrameMatrix& m = ws.slot_matrix(s);
+        off.push_back((int64_t)tmpl.size());
+        len.push_back(m.rows);
+        max_slot_len_ = std::max(max_slot_len_, m.rows);
+        tmpl.insert(tmpl.end(), m.v.begin(), m.v.end());
+    }
+    upload(tmpl_, tmpl, stream_, "templates");
+    upload(slot_off_, off, stream_, "slot offsets");
+    upload(slot_len_, len, stream_, "slot lengths");
+    upload(metas_, ws.metas, stream_, "wakeword metas");
+
+    if (d_ != old_d) {  // set_out_size (extractor.rs:47-59): new filter bank, extractor reset
+        MfccTables t = build_mfcc_tables(d_);
+        upload(hamming_, t.hamming, stream_, "hamming");
+        upload(tw480_, t.tw480, stream_, "twiddles");
+        upload(mel_bank_, t.mel_bank, stream_, "mel bank");
+        upload(centres_, t.centres, stream_, "mel centres");
+        upload(dct_, t.dct, stream_, "dct");
+        tables_.hamming = hamming_.as<float>();
+        tables_.tw480 = tw480_.as<float2>();
+        tables_.mel_bank = mel_bank_.as<float>();
+        tables_.centres = centres_.as<int>();
+        tables_.dct = dct_.as<float>();
+        tables_.num_coefficients = t.num_coefficients;
+        frames_[0].release();
+        frames_[1].release();
+        frames_cap_ = 0;
+        hist_ = 0;
+    }
+    // frame history: keep the most recent rows when max_frames changes
+    const int new_hist = std::max(max_frames_ - 1, 0);
+    if (new_hist != old_hist || frames_cap_ == 0) {
+        const int cap = std::max(frames_cap_, kHopsPerChunk);
+        DeviceBuffer nb[2];
+        const size_t rows = (size_t)new_hist + cap;
+        for (auto& b : nb) {
+            b.reserve((size_t)n_streams_ * rows * d_ * sizeof(float), "frame buffer");
+            cuda_check(cudaMemsetAsync(b.as<void>(), 0, b.bytes(), stream_), "memset frames");
+        }
+        if (frames_cap_ > 0 && d_ == old_d && old_hist > 0) {
+            const int keep = std::min(old_hist, new_hist);
+            const size_t old_rows = (size_t)old_hist + frames_cap_;
+            if (keep > 0)
+                cuda_check(launch_copy_rows(frames_[cur_].as<float>() + (size_t)(old_hist - keep) * d_, (int64_t)old_rows * d_,
+                                            nb[0].as<float>() + (size_t)(new_hist - keep) * d_, (int64_t)rows * d_, n_streams_,
+                                            (int64_t)keep * d_, stream_), "history move");
+        }
+        cuda_check(cudaStreamSynchronize(stream_), "sync");
+        frames_[0].swap(nb[0]);
+        frames_[1].swap(nb[1]);
+        cur_ = 0;
+        hist_ = new_hist;
+        frames_cap_ = cap;
+    }
+    cuda_check(cudaStreamSynchronize(stream_), "configure");
+}
+
+void Engine::ensure_frames(int n_new) {
+    if (n_new <= frames_cap_) return;
+    const size_t old_rows = (size_t)hist_ + frames_cap_, rows = (size_t)hist_ + n_new;
+    DeviceBuffer nb[2];
+    for (auto& b : nb) b.reserve((size_t)n_streams_ * rows * d_ * sizeof(float), "frame buffer");
+    cuda_check(cudaMemsetAsync(nb[0].as<void>(), 0, nb[0].bytes(), stream_), "memset frames");
+    if (hist_ > 0)
+        cuda_check(launch_copy_rows(frames_[cur_].as<float>(), (int64_t)old_rows * d_, nb[0].as<float>(), (int64_t)rows * d_,
+                                    n_streams_, (int64_t)hist_ * d_, stream_), "history move");
+    cuda_check(cudaStreamSynchronize(stream_), "sync");
+    frames_[0].swap(nb[0]);
+    frames_[1].swap(nb[1]);
+    cur_ = 0;
+    frames_cap_ = n_new;
+}
+
+void Engine::process(const float* audio, int64_t S, bool on_device, bool want_vad, std::vector<HitRecord>& hits,
+                     std::vector<float>* vad) {
+    hits.clear();
+    if (n_slots_ == 0) return;
+    cuda_check(cudaSetDevice(device_), "cudaSetDevice");
+    const int n_new = (int)(S / kHopSamples);
+    ensure_frames(n_new);
+    launches = 0;
+    const int64_t rows = (int64_t)hist_ + frames_cap_;
+    const size_t audio_bytes = (size_t)n_streams_ * S * sizeof(float);
+
+    cuda_check(cudaEventRecord(ev_[0], stream_), "event");
+    const float* src = audio;
+    if (!on_device) {
+        audio_.reserve(audio_bytes, "audio staging");
+        cuda_check(cudaMemcpyAsync(audio_.as<void>(), audio, audio_bytes, cudaMemcpyHostToDevice, stream_), "H2D audio");
+        src = audio_.as<float>();
+    }
+    cuda_check(cudaEventRecord(ev_[1], stream_), "event");
+
+    // K1: frame j of this call ends at new hop j and starts two hops earlier (carry or earlier audio)
+    float* vad_dev = nullptr;
+    if (want_vad) {
+        vad_.reserve((size_t)n_streams_ * n_new * sizeof(float), "vad values");
+        vad_dev = vad_.as<float>();
+    }
+    float* fb = frames_[cur_].as<float>();
+    cuda_check(launch_mfcc_frames(src, S, carry_.as<float>(), n_streams_, n_new, -2 * kHopSamples, tables_, fb, rows, hist_,
+                                  vad_dev, stream_), "mfcc kernel");
+    cuda_check(launch_copy_rows(src + (S - 2 * kHopSamples), S, carry_.as<float>(), 2 * kHopSamples, n_streams_,
+                                2 * kHopSamples, stream_), "carry update");
+    launches += 2;
+    cuda_check(cudaEventRecord(ev_[2], stream_), "event");
+
+    // K2: window scores; K3: judgement -> compact hit list
+    const int64_t n_windows = n_streams_ * (int64_t)n_new;
+    tscore_.reserve((size_t)n_windows * n_slots_ * sizeof(float), "window scores");
+    const int stride = 5 + max_templates_;
+    hits_.reserve((size_t)n_windows * stride * sizeof(float), "hit list");
+    cuda_check(cudaMemsetAsync(hit_count_.as<void>(), 0, sizeof(int), stream_), "memset");
+    DtwWindowsArgs wa;
+    wa.frames = fb;
+    wa.frame_rows = rows;
+    wa.first_window_row = hist_ - (max_frames_ - 1);
+    wa.n_new = n_new;
+    wa.n_streams = n_streams_;
+    wa.d = d_;
+    wa.tmpl = tmpl_.as<float>();
+    wa.slot_off = slot_off_.as<int64_t>();
+    wa.slot_len = slot_len_.as<int32_t>();
+    wa.n_slots = n_slots_;
+    wa.max_len = max_slot_len_;
+    wa.band = band_;
+    wa.score_ref = score_ref_;
+    wa.scores = tscore_.as<float>();
+    cuda_check(launch_dtw_windows_generic(wa, stream_), "dtw kernel");
+    JudgeArgs ja;
+    ja.scores = tscore_.as<float>();
+    ja.n_streams = n_streams_;
+    ja.n_new = n_new;
+    ja.n_slots = n_slots_;
+    ja.metas = metas_.as<WakewordMeta>();
+    ja.n_wakewords = n_wakewords_;
+    ja.score_mode = score_mode_;
+    ja.max_templates = max_templates_;
+    ja.hit_count = hit_count_.as<int>();
+    ja.hits = hits_.as<float>();
+    ja.capacity = n_windows;
+    cuda_check(launch_judge_windows(ja, stream_), "judge kernel");
+    // next call's history = the last hist_ rows of [history | new frames]
+    if (hist_ > 0)
+        cuda_check(launch_copy_rows(fb + (size_t)n_new * d_, rows * d_, frames_[1 - cur_].as<float>(), rows * d_, n_streams_,
+                                    (int64_t)hist_ * d_, stream_), "history move");
+    cur_ ^= 1;
+    launches += 3;
+    last_n_new_ = n_new;
+    cuda_check(cudaEventRecord(ev_[3], stream_), "event");
+
+    // D2H: count, then the records
+    cuda_check(cudaMemcpyAsync(count_host_, hit_count_.as<void>(), sizeof(int), cudaMemcpyDeviceToHost, stream_), "D2H count");
+    cuda_check(cudaStreamSynchronize(stream_), "sync");
+    const int n_hits = (int)std::min<int64_t>(*count_host_, n_windows);
+    if (n_hits > 0) {
+        const size_t need = (size_t)n_hits * stride;
+        if (need > hit_host_floats_) {
+            if (hit_host_) cudaFreeHost(hit_host_);
+            hit_host_ = nullptr;
+            hit_host_floats_ = 0;
+            cuda_check(cudaMallocHost(&hit_host_, need * 2 * sizeof(float)), "cudaMallocHost hits");
+            hit_host_floats_ = need * 2;
+        }
+        cuda_check(cudaMemcpyAsync(hit_host_, hits_.as<void>(), need * sizeof(float), cudaMemcpyDeviceToHost, stream_), "D2H hits");
+    }
+    if (want_vad && vad) {
+        vad->resize((size_t)n_windows);
+        cuda_check(cudaMemcpyAsync(vad->data(), vad_dev, (size_t)n_windows * sizeof(float), cudaMemcpyDeviceToHost, stream_), "D2H vad");
+    }
+    cuda_check(cudaEventRecord(ev_[4], stream_), "event");
+    cuda_check(cudaStreamSynchronize(stream_), "sync");
+    for (int i = 0; i < 4; i++) cudaEventElapsedTime(&timings_ms[i], ev_[i], ev_[i + 1]);
+
+    hits.resize((size_t)n_hits);
+    for (int i = 0; i < n_hits; i++) {
+        const float* rec = hit_host_ + (size_t)i * stride;
+        HitRecord& h = hits[i];
+        std::memcpy(&h.stream, rec + 0, 4);
+        std::memcpy(&h.frame, rec + 1, 4);
+        std::memcpy(&h.wakeword, rec + 2, 4);
+        h.avg_score = rec[3];
+        h.score = rec[4];
+        h.scores = rec + 5;
+    }
+    std::sort(hits.begin(), hits.end(), [](const HitRecord& a, const HitRecord& b) {
+        return a.stream != b.stream ? a.stream < b.stream : a.frame < b.frame;
+    });
+}
+
+}  // namespace rp

@@ -1,0 +1,110 @@
+// Device side of one batch of streams: buffers resident in HBM, the per-call launch sequence
+// (H2D -> K1 MFCC -> K2 DTW window scores -> K3 judge -> D2H of the compact hit list).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "mfcc_tables.h"
+#include "rp_internal.h"
+#include "stream_state.h"
+
+namespace rp {
+
+void cuda_check(cudaError_t e, const char* what);
+
+class DeviceBuffer {
+  public:
+    DeviceBuffer() = default;
+    DeviceBuffer(const DeviceBuffer&) = delete;
+    DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+    ~DeviceBuffer();
+    // grows (never shrinks); contents are NOT preserved on growth
+    void reserve(size_t bytes, const char* what);
+    void release();
+    void swap(DeviceBuffer& o) {
+        void* p = p_; p_ = o.p_; o.p_ = p;
+        size_t b = bytes_; bytes_ = o.bytes_; o.bytes_ = b;
+    }
+    template <typename T> T* as() const { return static_cast<T*>(p_); }
+    size_t bytes() const { return bytes_; }
+  private:
+    void* p_ = nullptr;
+    size_t bytes_ = 0;
+};
+
+struct HitRecord {     // one judged detection of K3, host copy
+    int32_t stream, frame, wakeword;
+    float avg_score, score;
+    const float* scores;  // into Engine::hit_host_
+};
+
+class Engine {
+  public:
+    Engine(int device, int64_t n_streams);
+    ~Engine();
+    Engine(const Engine&) = delete;
+
+    int device() const { return device_; }
+    int64_t n_streams() const { return n_streams_; }
+    void set_cuda_stream(cudaStream_t s);  // caller-owned stream (nullptr restores the private one)
+    cudaStream_t cuda_stream() const { return stream_; }
+
+    // Uploads templates / tables for the wakeword set; keeps per-stream frame history.
+    void configure(const WakewordSet& ws, const rp_config& cfg);
+    void set_dtw_variant(int v) { dtw_variant_ = v; }
+
+    // Scores samples_per_stream/160 new hops per stream. Returns the hits sorted by (stream, frame);
+    // `vad` (if want_vad) receives [n_streams][n_hops] mean |mfcc| per new frame.
+    void process(const float* audio, int64_t samples_per_stream, bool on_device, bool want_vad,
+                 std::vector<HitRecord>& hits, std::vector<float>* vad);
+
+    // diagnostics
+    float timings_ms[5] = {0, 0, 0, 0, 0};
+    int launches = 0;
+    // dense scores of the last call [n_streams][n_new][n_slots] (device) — parity tests read it
+    const float* last_scores_dev() const { return tscore_.as<float>(); }
+    const float* last_frames_dev(int64_t* rows_per_stream, int* first_new_row) const;
+    int n_slots() const { return n_slots_; }
+
+  private:
+    void ensure_frames(int n_new);
+
+    int device_ = 0;
+    int64_t n_streams_ = 0;
+    cudaStream_t stream_ = nullptr, own_stream_ = nullptr;
+    cudaEvent_t ev_[6] = {};
+    int dtw_variant_ = 0;
+
+    // wakeword set on device
+    int d_ = 0, max_frames_ = 0, n_slots_ = 0, n_wakewords_ = 0, max_templates_ = 0, max_slot_len_ = 0;
+    int band_ = 5, score_mode_ = 1;
+    float score_ref_ = 0.22f;
+    DeviceBuffer tmpl_, slot_off_, slot_len_, metas_;
+    // MFCC tables on device
+    DeviceBuffer hamming_, tw480_, mel_bank_, centres_, dct_;
+    MfccTablesDev tables_;
+    // per-stream state
+    DeviceBuffer carry_;       // [B][320] last two hops of audio
+    DeviceBuffer frames_[2];   // [B][hist_ + frames_cap_][d]
+    int cur_ = 0;
+    int hist_ = 0;             // history rows kept in front of the new frames (= max_frames - 1)
+    int frames_cap_ = 0;       // new-frame capacity per stream
+    // per-call
+    DeviceBuffer audio_;       // [B][S] staging for host audio
+    DeviceBuffer tscore_;      // [B][n_new][n_slots]
+    DeviceBuffer vad_;         // [B][n_new]
+    DeviceBuffer hits_;        // [cap][5 + max_templates]
+    DeviceBuffer hit_count_;   // int
+    int last_n_new_ = 0;
+    // pinned host staging for the hit list
+    float* hit_host_ = nullptr;
+    size_t hit_host_floats_ = 0;
+    int* count_host_ = nullptr;
+};
+
+}  // namespace rp

@@ -1,0 +1,92 @@
+// Launchers of the CUDA kernels (defined in mfcc_kernel.cu / dtw_kernel.cu / score_kernel.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "score_logic.h"
+
+namespace rp {
+
+// Device-resident MFCC tables (see mfcc_tables.h)
+struct MfccTablesDev {
+    const float* hamming = nullptr;   // [480]
+    const float2* tw480 = nullptr;    // [480] exp(-2 pi i k / 480)
+    const float* mel_bank = nullptr;  // [C][240]
+    const int* centres = nullptr;     // [C+2]
+    const float* dct = nullptr;       // [C][C]
+    int num_coefficients = 0;         // C
+};
+
+// K1. Frame j of stream b is built from the 480 samples starting at logical sample
+// 160*j + sample_offset0 of that stream, where logical sample i is audio[b*audio_stride + i] for
+// i >= 0 and carry[b*320 + 320 + i] for -320 <= i < 0 (the two hops kept from the previous call).
+// out[(b*out_stride_frames + out_row0 + j) * D + k], k < D = C-1.  vad_out (optional):
+// [(b*frames_per_stream + j)] = mean |mfcc| of the frame (src/mfcc/vad.rs:12).
+cudaError_t launch_mfcc_frames(const float* audio, int64_t audio_stride, const float* carry, int64_t n_streams,
+                               int frames_per_stream, int sample_offset0, const MfccTablesDev& t, float* out,
+                               int64_t out_stride_frames, int out_row0, float* vad_out, cudaStream_t stream);
+
+// Describes the DTW work of one launch of the generic kernel.
+struct DtwPairsArgs {
+    const float* tmpl = nullptr;       // template rows
+    const int64_t* tmpl_off = nullptr; // per pair offset in floats, or nullptr => p * tmpl_len_max * d
+    const int32_t* tmpl_len = nullptr; // per pair rows, or nullptr => tmpl_len_max
+    int tmpl_len_max = 0;
+    const float* win = nullptr;
+    const int64_t* win_off = nullptr;
+    const int32_t* win_len = nullptr;
+    int win_len_max = 0;
+    int64_t n_pairs = 0;
+    int d = 0;
+    int band = 5;
+    float score_ref = 0.22f;
+    int cmn = 0;                       // apply MfccNormalizer::normalize to the window
+    float* out = nullptr;
+};
+// K2 generic ("faithful") kernel: one warp per pair, anti-diagonal wavefront, reference operation order.
+cudaError_t launch_dtw_pairs_generic(const DtwPairsArgs& a, cudaStream_t stream);
+
+// Pipeline scoring: every new frame j of every stream closes a window; slot s scores the first
+// slot_len[s] frames of that window (after CMN) against template s.
+struct DtwWindowsArgs {
+    const float* frames = nullptr;     // [n_streams][frame_rows][d]
+    int64_t frame_rows = 0;            // rows per stream in `frames` (history + new)
+    int first_window_row = 0;          // row of the first frame of the window that ends at new frame 0
+    int n_new = 0;                     // new frames (= windows) per stream
+    int64_t n_streams = 0;
+    int d = 0;
+    const float* tmpl = nullptr;       // all slots' template rows, packed
+    const int64_t* slot_off = nullptr; // [n_slots] offset in floats
+    const int32_t* slot_len = nullptr; // [n_slots] rows
+    int n_slots = 0;
+    int max_len = 0;                   // max slot_len
+    int band = 5;
+    float score_ref = 0.22f;
+    float* scores = nullptr;           // [n_streams][n_new][n_slots]
+};
+cudaError_t launch_dtw_windows_generic(const DtwWindowsArgs& a, cudaStream_t stream);
+
+// K3: judge every window, append detections to a compact hit list.
+// hit record (floats/ints, stride = 5 + max_templates): [stream, frame, wakeword, avg_score, score, scores...]
+struct JudgeArgs {
+    const float* scores = nullptr;     // [n_streams][n_new][n_slots]
+    int64_t n_streams = 0;
+    int n_new = 0;
+    int n_slots = 0;
+    const WakewordMeta* metas = nullptr;  // device
+    int n_wakewords = 0;
+    int score_mode = 1;
+    int max_templates = 0;
+    int* hit_count = nullptr;          // device counter (zeroed by the caller)
+    float* hits = nullptr;             // device [capacity][5 + max_templates]
+    int64_t capacity = 0;
+};
+cudaError_t launch_judge_windows(const JudgeArgs& a, cudaStream_t stream);
+
+// misc small kernels
+cudaError_t launch_copy_rows(const float* src, int64_t src_stride, float* dst, int64_t dst_stride, int64_t n_streams,
+                             int64_t row_floats, cudaStream_t stream);
+
+}  // namespace rp

@@ -62,3 +62,53 @@ def synth_audio(n_streams: int, n_samples: int, seed: int = 0x5EED) -> np.ndarra
         x[x == 0] = np.float32(1e-4)
         out[b] = x
     return out
+
+
+def synth_utterance(seed: int, n_frames: int) -> np.ndarray:
+    """A deterministic speech-like burst: three gliding formants with an amplitude envelope plus a
+    little noise; (n_frames + 3) hops long so a fresh MfccExtractor emits exactly n_frames frames."""
+    rng = np.random.default_rng(seed)
+    n = (n_frames + 3) * 160
+    t = np.arange(n) / 16000.0
+    x = np.zeros(n)
+    for k in range(3):
+        f0 = rng.uniform(250, 900) * (k + 1)
+        f1 = f0 * rng.uniform(0.6, 1.6)
+        ph = 2 * np.pi * (f0 * t + 0.5 * (f1 - f0) / t[-1] * t * t)
+        am = 0.5 + 0.5 * np.sin(2 * np.pi * rng.uniform(2, 7) * t + rng.uniform(0, 6))
+        x += (0.25 / (k + 1)) * am * np.sin(ph)
+    env = np.sin(np.pi * np.arange(n) / n) ** 0.5
+    x = x * env + 0.01 * rng.standard_normal(n)
+    x = np.clip(x, -1, 1).astype(np.float32)
+    x[x == 0] = np.float32(1e-4)
+    return x
+
+
+def make_wakeword(oracle, name="hey b200", d=16, lengths=(88, 92, 96, 100, 100, 96, 92, 100), seed=1234,
+                  threshold=None, avg_threshold=None, with_avg=True):
+    """Synthetic WakewordRef: templates are the ORACLE's MFCC + CMN of synthetic
+    utterances (so they are realistic mean-normalised cepstra). Returns (rpw bytes, utterances)."""
+    utts, tmpl = [], []
+    base = synth_utterance(seed, max(lengths))
+    for i, n in enumerate(lengths):
+        # variations of one "word": time-trimmed, slightly noised copies of the base utterance
+        rng = np.random.default_rng(seed + 17 * i + 1)
+        off = int(rng.integers(0, max(lengths) - n + 1)) * 160
+        u = base[off: off + (n + 3) * 160].copy()
+        u = np.clip(u * np.float32(rng.uniform(0.8, 1.1)) + 0.004 * rng.standard_normal(u.size).astype(np.float32), -1, 1)
+        u = u.astype(np.float32)
+        u[u == 0] = np.float32(1e-4)
+        utts.append(u)
+        tmpl.append((f"sample_{i}.wav", oracle.normalize(oracle.mfcc_stream(u, d))))
+    avg = None
+    if with_avg:
+        longest = max(tmpl, key=lambda t: t[1].shape[0])[1]
+        avg = longest.copy()
+    rpw = oracle.encode_wakeword(name, tmpl, avg=avg, rms_level=0.05, threshold=threshold, avg_threshold=avg_threshold)
+    return rpw, utts
+
+
+def splice(audio: np.ndarray, utt: np.ndarray, hop_offset: int) -> None:
+    """Overwrites audio[hop_offset*160 : ...] with an utterance (in place)."""
+    s = hop_offset * 160
+    audio[s: s + utt.size] = utt

@@ -1,0 +1,330 @@
+"""Parity of the CUDA path against the oracle and the reference goldens — runs on the B200 box
+(`-m gpu`). Everything goes through the C ABI (rustpotter_b200.api is a ctypes binding).
+
+Tolerances: north_star asks for scores within 1e-4 relative of the reference's CPU output; the
+generic DTW kernel follows the reference's operation order so it is held to 5e-6; MFCC coefficients
+are compared absolutely (they are O(10..100); silent frames are pure rounding noise).
+"""
+import numpy as np
+import pytest
+
+import rustpotter_b200 as rp
+from oracle import oracle as O
+from tests.helpers import (golden, make_wakeword, read_wav_i16, run_detection_simulation, splice, synth_audio,
+                           synth_utterance, two_wakeword_stream)
+
+pytestmark = pytest.mark.gpu
+SCORE_RTOL = 1e-4
+
+
+def _torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+# ------------------------------------------------------------------ K1
+@pytest.mark.parametrize("d", [5, 16, 13, 31])
+def test_mfcc_kernel_matches_oracle(d):
+    torch = _torch()
+    audio = synth_audio(5, 160 * 131, seed=11)
+    got = rp.mfcc_frames(torch.from_numpy(audio).cuda(), d).cpu().numpy()
+    assert got.shape == (5, 128, d)
+    for b in range(5):
+        want = O.mfcc_stream(audio[b], d)
+        err = np.abs(got[b] - want)
+        assert err.max() < 1e-3, (d, b, err.max(), np.unravel_index(err.argmax(), err.shape))
+
+
+def test_mfcc_kernel_reproduces_reference_templates():
+    """wav -> kernel MFCC -> CMN equals the matrices stored in the reference's .rpw (its own output)."""
+    torch = _torch()
+    ww = dict(O.Wakeword(open(golden("oye_casa_g.rpw"), "rb").read()).templates)
+    for i in range(1, 6):
+        s = read_wav_i16(golden(f"oye_casa_g_{i}.wav")).astype(np.float32) / np.float32(32767.0)
+        s = s[: len(s) // 480 * 480]
+        m = rp.mfcc_frames(torch.from_numpy(s[None]).cuda(), 5).cpu().numpy()[0]
+        m = O.normalize(m)
+        t = ww[f"oye_casa_g_{i}.wav"]
+        assert m.shape == t.shape and np.abs(m - t).max() < 2e-4, (i, np.abs(m - t).max())
+
+
+def test_mfcc_edge_cases():
+    torch = _torch()
+    # too short for any frame: 3 hops -> 0 frames (extractor.rs:69-79)
+    out = rp.mfcc_frames(torch.zeros((2, 480), device="cuda"), 16)
+    assert out.shape == (2, 0, 16)
+    # digital silence: every coefficient is rounding noise around 0 (|c| tiny), never NaN/inf
+    out = rp.mfcc_frames(torch.zeros((1, 160 * 10), device="cuda"), 16).cpu().numpy()
+    assert np.isfinite(out).all() and np.abs(out).max() < 1e-2
+    want = O.mfcc_stream(np.zeros(1600, np.float32), 16)
+    assert np.abs(out[0] - want).max() < 1e-3
+    # full-scale square wave (clipping input), one stream
+    x = np.sign(np.sin(np.arange(160 * 40) * 0.05)).astype(np.float32)
+    got = rp.mfcc_frames(torch.from_numpy(x[None]).cuda(), 16).cpu().numpy()[0]
+    assert np.abs(got - O.mfcc_stream(x, 16)).max() < 2e-3
+
+
+# ------------------------------------------------------------------ K2
+def _rel(a, b):
+    return abs(float(a) - float(b)) / max(abs(float(b)), 1e-12)
+
+
+@pytest.mark.parametrize("m,n,d,band,cmn", [
+    (100, 100, 16, 5, True), (120, 100, 16, 5, False), (100, 120, 16, 5, False), (93, 93, 5, 5, True),
+    (108, 108, 5, 2, True), (50, 50, 16, 1, False), (64, 70, 13, 9, True), (30, 30, 16, 40, False),
+    (3, 3, 16, 5, True), (1, 1, 16, 5, False), (2, 1, 4, 5, False), (168, 168, 5, 5, True), (100, 100, 31, 5, True),
+])
+def test_dtw_kernel_matches_oracle(m, n, d, band, cmn):
+    torch = _torch()
+    rng = np.random.default_rng(m * 1000 + n + d)
+    P = 24
+    scale = np.array([8, 4, 3, 2, 2, 1.5] + [1.0] * 40, np.float32)[:d]
+    a = (rng.standard_normal((P, m, d)) * scale).astype(np.float32)
+    w = (rng.standard_normal((P, n, d)) * scale + (3.0 if cmn else 0.0)).astype(np.float32)
+    a[1] = a[0]                                   # identical pair content
+    if m == n:
+        w[1] = a[1]
+    a[2, m // 2] = 0.0                            # zero vector inside a template (similarity 0 rule)
+    w[3, :] = 0.0                                 # all-zero window
+    got = rp.dtw_scores(torch.from_numpy(a).cuda(), torch.from_numpy(w).cuda(), band=band, cmn=cmn).cpu().numpy()
+    for p in range(P):
+        wb = O.normalize(w[p]) if cmn else w[p]
+        ref = O.compare(a[p], wb, band, 0.22)
+        if ref == 0.0:
+            assert got[p] == 0.0, (p, got[p])
+        else:
+            assert _rel(got[p], ref) < 5e-6, (p, got[p], ref)
+
+
+def test_dtw_ragged_pairs():
+    torch = _torch()
+    rng = np.random.default_rng(9)
+    d = 16
+    lens_a = [90, 100, 120, 77, 100, 35]
+    lens_b = [90, 100, 100, 77, 104, 35]
+    A = [rng.standard_normal((l, d)).astype(np.float32) for l in lens_a]
+    Bm = [rng.standard_normal((l, d)).astype(np.float32) for l in lens_b]
+    fa, fb = np.concatenate([x.ravel() for x in A]), np.concatenate([x.ravel() for x in Bm])
+    oa = np.cumsum([0] + [x.size for x in A[:-1]]).astype(np.int64)
+    ob = np.cumsum([0] + [x.size for x in Bm[:-1]]).astype(np.int64)
+    t = lambda x, dt: torch.from_numpy(np.asarray(x, dt)).cuda()  # noqa: E731
+    got = rp.dtw_scores(t(fa, np.float32), t(fb, np.float32), band=5, cmn=True, tmpl_off=t(oa, np.int64),
+                        tmpl_len=t(lens_a, np.int32), win_off=t(ob, np.int64), win_len=t(lens_b, np.int32),
+                        max_tmpl_len=max(lens_a), max_win_len=max(lens_b), d=d, n_pairs=len(A)).cpu().numpy()
+    for p in range(len(A)):
+        ref = O.compare(A[p], O.normalize(Bm[p]), 5, 0.22)
+        assert (got[p] == 0.0 and ref == 0.0) or _rel(got[p], ref) < 5e-6, (p, got[p], ref)
+
+
+def test_dtw_size_independent_properties():
+    """At bench scale (no oracle): identical sequences give exactly 1/(1+e^-1) when the last two
+    template rows coincide; scores are invariant to positive per-row scaling (cosine distance)."""
+    torch = _torch()
+    P, m, d = 20000, 100, 16
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn((P, m, d), device="cuda", generator=g)
+    a[:, -2] = a[:, -1]
+    s = rp.dtw_scores(a, a.clone(), band=5)
+    assert torch.allclose(s, torch.full_like(s, 0.7310586), atol=2e-6)
+    w = torch.randn((P, m, d), device="cuda", generator=g)
+    s1 = rp.dtw_scores(a, w, band=5)
+    s2 = rp.dtw_scores(a * 3.0, w * 0.25, band=5)
+    assert torch.allclose(s1, s2, rtol=2e-5, atol=1e-7)
+    assert float(s1.min()) > 0.0 and float(s1.max()) < 0.7311
+
+
+# ------------------------------------------------------------------ detector goldens through the C ABI
+def _sim(rpw, gains=(1.0, 1.0), **cfg):
+    det = rp.Rustpotter(rp.default_config(sample_rate=16000, sample_format="i16", channels=1, **cfg))
+    det.add_wakeword_from_file("wakeword", golden(rpw))
+    return run_detection_simulation(det, two_wakeword_stream(*gains))
+
+
+def _check(dets, expected):
+    assert len(dets) == len(expected), dets
+    for d, e in zip(dets, expected):
+        for k, v in e.items():
+            assert abs(float(d[k]) - v) <= SCORE_RTOL * abs(v), (k, d[k], v)
+
+
+BASE = dict(avg_threshold=0.2, threshold=0.5)
+
+
+def test_golden_v2_file():  # reference tests/detector.rs:9-22
+    _check(_sim("oye_casa_g_v2.rpw", score_mode="max", **BASE),
+           [dict(avg_score=0.6495044, score=0.7310586), dict(avg_score=0.5804737, score=0.721843)])
+
+
+def test_golden_max():  # :25-38
+    _check(_sim("oye_casa_g.rpw", score_mode="max", **BASE),
+           [dict(avg_score=0.6495044, score=0.7310586), dict(avg_score=0.5804737, score=0.721843)])
+
+
+def test_golden_median():  # :41-54
+    _check(_sim("oye_casa_g.rpw", score_mode="median", **BASE),
+           [dict(avg_score=0.64608675, score=0.60123634), dict(avg_score=0.5288923, score=0.63968724)])
+
+
+def test_golden_average():  # :57-70
+    _check(_sim("oye_casa_g.rpw", score_mode="average", **BASE),
+           [dict(avg_score=0.64608675, score=0.60458726), dict(avg_score=0.5750509, score=0.6313083)])
+
+
+def test_golden_vad():  # :73-87
+    _check(_sim("oye_casa_g.rpw", score_mode="max", vad_mode="easy", **BASE),
+           [dict(avg_score=0.6495044, score=0.7310586), dict(avg_score=0.5804737, score=0.721843)])
+
+
+def test_golden_ignore_words():  # :90-100
+    assert _sim("alexa.rpw", score_mode="max", avg_threshold=0.0, threshold=0.45, min_scores=0) == []
+
+
+def test_golden_ignore_words_with_filters():  # :102-112
+    assert _sim("alexa.rpw", score_mode="max", avg_threshold=0.0, threshold=0.45, min_scores=0,
+                gain_normalizer_enabled=1, band_pass_enabled=1) == []
+
+
+def test_golden_band_pass():  # :114-127
+    _check(_sim("oye_casa_g.rpw", score_mode="max", avg_threshold=0.0, threshold=0.5, band_pass_enabled=1,
+                low_cutoff=80.0, high_cutoff=400.0), [dict(score=0.6858197), dict(score=0.66327363)])
+
+
+def test_golden_gain_normalizer():  # :130-142
+    _check(_sim("oye_casa_g.rpw", gains=(0.2, 5.0), score_mode="max", avg_threshold=0.0, threshold=0.5,
+                gain_normalizer_enabled=1), [dict(score=0.7304294), dict(score=0.71067876)])
+
+
+def test_golden_gain_and_band_pass():  # :145-159
+    _check(_sim("oye_casa_g.rpw", gains=(0.2, 5.0), score_mode="median", avg_threshold=0.0, threshold=0.5,
+                gain_normalizer_enabled=1, band_pass_enabled=1, low_cutoff=80.0, high_cutoff=500.0),
+           [dict(score=0.5775406), dict(score=0.5828697)])
+
+
+def test_detector_matches_oracle_detector_fully():
+    """Same stream through the product and the oracle: identical detections (names, counters,
+    per-template scores) — stronger than the reference's own asserts."""
+    for kw in (dict(score_mode="max"), dict(score_mode="p75", min_scores=2, eager=1), dict(score_mode="median", vad_mode="medium")):
+        cfg = dict(sample_format="i16", **kw)
+        a = rp.Rustpotter(rp.default_config(**cfg))
+        b = O.Detector(O.default_config(**cfg))
+        for x in (a, b):
+            x.add_wakeword_from_file("wakeword", golden("oye_casa_g.rpw"))
+        stream = two_wakeword_stream()
+        da, db = run_detection_simulation(a, stream), run_detection_simulation(b, stream)
+        assert len(da) == len(db) and len(da) >= 1
+        for x, y in zip(da, db):
+            assert x["name"] == y["name"] and x["counter"] == y["counter"], (x, y)
+            assert _rel(x["score"], y["score"]) < SCORE_RTOL and _rel(x["avg_score"], y["avg_score"]) < SCORE_RTOL
+            for k in y["scores"]:
+                assert _rel(x["scores"][k], y["scores"][k]) < SCORE_RTOL
+        assert a.windows_scored() == b.windows_scored()
+
+
+def test_api_error_behaviour():
+    det = rp.Rustpotter(rp.default_config(sample_format="i16"))
+    assert det.process_samples(np.zeros(480, np.int16)) is None          # no wakeword: None (detector.rs:348-350)
+    det.add_wakeword_from_file("w", golden("oye_casa_g.rpw"))
+    assert det.get_samples_per_frame() == 480 and det.get_bytes_per_frame() == 960
+    assert det.process_bytes(bytes(100)) is None                          # wrong length: None (:235-237)
+    assert det.process_samples(np.zeros(479, np.int16)) is None
+    with pytest.raises(rp.RustpotterError) as e:                          # mfcc size mismatch (:308-320)
+        det.add_wakeword_from_buffer("w16", make_wakeword(O, d=16, lengths=(20, 24))[0])
+    assert e.value.code == -5
+    with pytest.raises(rp.RustpotterError):
+        det.add_wakeword_from_buffer("bad", b"\x01\x02")
+    assert det.remove_wakeword("nope") is False and det.remove_wakeword("w") is True and det.remove_wakewords() is False
+    with pytest.raises(rp.RustpotterError) as e:
+        rp.Rustpotter(rp.default_config(sample_rate=48000))               # resampler is out of scope
+    assert e.value.code == -4
+    # stereo i32 big-endian bytes: channel 0 is used
+    d2 = rp.Rustpotter(rp.default_config(sample_format="i32", channels=2, endianness="big"))
+    assert d2.get_samples_per_frame() == 960 and d2.get_bytes_per_frame() == 3840
+
+
+# ------------------------------------------------------------------ batched front-end
+def _batch_case(B=12, n_chunks=150, seed=21, **cfgkw):
+    rpw, utts = make_wakeword(O, d=16, seed=seed)
+    audio = synth_audio(B, n_chunks * 480, seed=seed)
+    for b in range(0, B, 3):
+        splice(audio[b], utts[(b // 3) % len(utts)], 150 + 7 * b)
+    if B > 4:
+        splice(audio[4], utts[1], 40)
+        splice(audio[4], utts[2], 260)     # two utterances in one stream
+    return rpw, audio, cfgkw
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(score_mode="median", min_scores=2), dict(score_mode="average", eager=1, min_scores=3),
+                                dict(avg_threshold=0.0, threshold=0.35, min_scores=1)])
+def test_batch_matches_oracle_streams(kw):
+    rpw, audio, _ = _batch_case()
+    total, counts, want = O.run_streams(O.default_config(**kw), [rpw], audio, n_threads=4, max_det=8)
+    bt = rp.RustpotterBatch(audio.shape[0], rp.default_config(**kw))
+    bt.add_wakeword_from_buffer("w0", rpw)
+    got = bt.process(audio)
+    assert counts.sum() >= 3, "test data must produce detections"
+    per = {b: [] for b in range(audio.shape[0])}
+    for s, c, d in got:
+        per[s].append((c, d))
+    for b in range(audio.shape[0]):
+        assert len(per[b]) == int(counts[b]), (b, per[b], want[b])
+        for (c, d), w in zip(per[b], want[b]):
+            assert d["name"] == w["name"] and d["counter"] == w["counter"], (b, d, w)
+            assert _rel(d["score"], w["score"]) < SCORE_RTOL and _rel(d["avg_score"], w["avg_score"]) < SCORE_RTOL
+            for k in w["scores"]:
+                assert _rel(d["scores"][k], w["scores"][k]) < SCORE_RTOL
+    assert bt.windows_scored() == total
+
+
+def test_batch_vad_on_golden_stream():
+    """VAD needs true silence to say "no voice" (mean |mfcc| is scale invariant), so the batched VAD
+    path is exercised on the reference's own test stream, two copies, against the oracle."""
+    x = np.frombuffer(two_wakeword_stream(), dtype="<i2").astype(np.float32) / np.float32(32767.0)
+    x = x[: x.size // 480 * 480]
+    audio = np.stack([x, x])
+    rpw = open(golden("oye_casa_g.rpw"), "rb").read()
+    for mode in ("easy", "hard"):
+        total, counts, want = O.run_streams(O.default_config(vad_mode=mode), [rpw], audio, n_threads=2, max_det=4)
+        bt = rp.RustpotterBatch(2, rp.default_config(vad_mode=mode))
+        bt.add_wakeword_from_buffer("w", rpw)
+        got = bt.process(audio)
+        assert counts.tolist() == [2, 2] and len(got) == 4
+        for (s, c, d), w in zip(got, want[0] + want[1]):
+            assert _rel(d["score"], w["score"]) < SCORE_RTOL and _rel(d["avg_score"], w["avg_score"]) < SCORE_RTOL
+        assert bt.windows_scored() == total
+
+
+def test_batch_streaming_equals_bulk():
+    """Feeding the same audio in one call, in 7-chunk calls, and chunk by chunk gives the same
+    detections (state carried in HBM between calls)."""
+    rpw, audio, _ = _batch_case(B=6, n_chunks=140)
+    res = []
+    for step in (140, 7, 1):
+        bt = rp.RustpotterBatch(audio.shape[0])
+        bt.add_wakeword_from_buffer("w0", rpw)
+        out = []
+        for c0 in range(0, 140, step):
+            for s, c, d in bt.process(audio[:, c0 * 480:(c0 + step) * 480]):
+                out.append((s, c0 + c, d["counter"], float(d["score"])))
+        res.append((sorted(out), bt.windows_scored()))
+    assert res[0][0] and res[0] == res[1] == res[2]
+
+
+def test_batch_two_wakewords_and_device_audio():
+    torch = _torch()
+    rpw_a, utts_a = make_wakeword(O, name="alpha", d=16, seed=100)
+    rpw_b, utts_b = make_wakeword(O, name="beta", d=16, seed=200, lengths=(70, 80, 110, 76), with_avg=False, threshold=0.45)
+    audio = synth_audio(5, 200 * 480, seed=3)
+    splice(audio[0], utts_a[0], 200)
+    splice(audio[1], utts_b[2], 300)
+    splice(audio[3], utts_b[0], 100)
+    splice(audio[3], utts_a[3], 380)
+    total, counts, want = O.run_streams(O.default_config(), [rpw_a, rpw_b], audio, n_threads=2, max_det=8)
+    bt = rp.RustpotterBatch(5)
+    bt.add_wakeword_from_buffer("w0", rpw_a)
+    bt.add_wakeword_from_buffer("w1", rpw_b)
+    assert bt.max_mfcc_frames() == 110
+    got = bt.process(torch.from_numpy(audio).cuda())
+    assert sorted((s, d["name"], d["counter"]) for s, c, d in got) == sorted(
+        (b, w["name"], w["counter"]) for b in range(5) for w in want[b])
+    assert len(got) >= 3 and bt.windows_scored() == total

@@ -1,0 +1,176 @@
+"""CPU tests of the product's host side (no GPU, no compute calls): the C-ABI library loads and
+exports every symbol the header declares; the .rpw reader agrees with the oracle's; the per-stream
+state machine (detector.rs:377-454), fed the oracle's per-window scores, emits exactly the oracle
+detector's detections."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import rustpotter_b200 as rp
+from oracle import oracle as O
+from rustpotter_b200 import api
+from tests.helpers import ROOT, golden, read_wav_i16, two_wakeword_stream
+
+RPWS = ["oye_casa_g.rpw", "oye_casa_g_v2.rpw", "alexa.rpw", "oye_casa_real.rpw"]
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "rustpotter_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(rp_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared, "no declarations parsed"
+    L = rp.lib()
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in the header but not exported"
+    assert sorted(api.EXPORTED) == declared
+
+
+def test_defaults_match_reference():  # src/config.rs Default impls, src/constants.rs
+    c = rp.default_config()
+    assert (c.sample_rate, c.sample_format, c.channels, c.endianness) == (16000, 3, 1, 0)
+    assert abs(c.avg_threshold - 0.2) < 1e-7 and abs(c.threshold - 0.5) < 1e-7 and c.min_scores == 5 and c.eager == 0
+    assert abs(c.score_ref - 0.22) < 1e-7 and c.band_size == 5 and c.score_mode == 1 and c.vad_mode == -1
+    assert c.gain_normalizer_enabled == 0 and abs(c.min_gain - 0.1) < 1e-7 and c.max_gain == 1.0
+    assert c.band_pass_enabled == 0 and c.low_cutoff == 80.0 and c.high_cutoff == 400.0
+    o = O.default_config()
+    assert bytes(c) == bytes(o)  # identical layout and defaults as the oracle's twin struct
+
+
+@pytest.mark.skipif(rp.device_count() > 0, reason="checks the no-GPU failure mode")
+def test_create_fails_loudly_without_gpu():
+    h = C.c_void_p()
+    cfg = rp.default_config()
+    assert rp.lib().rp_create(C.byref(cfg), 0, C.byref(h)) == -2  # RP_ERR_CUDA
+    assert b"no CPU fallback" in rp.lib().rp_last_error(None)
+    with pytest.raises(rp.RustpotterError):
+        rp.Rustpotter()
+    with pytest.raises(rp.RustpotterError):
+        rp.RustpotterBatch(4)
+
+
+@pytest.mark.parametrize("name", RPWS)
+def test_rpw_reader_matches_oracle(name):
+    buf = open(golden(name), "rb").read()
+    info = rp.wakeword_inspect(buf)
+    ow = O.Wakeword(buf)
+    assert info["name"] == ow.name and info["mfcc_size"] == ow.mfcc_size and info["n_templates"] == len(ow.templates)
+    assert info["is_v2"] == (1 if "v2" in name else 0)
+    assert np.float32(info["rms_level"]) == ow.rms_level
+    assert info["has_threshold"] == int(ow.threshold is not None)
+    assert info["max_frames"] == max(t.shape[0] for _, t in ow.templates)
+    for t, (tn, tm) in enumerate(ow.templates):
+        n, m = rp.wakeword_template(buf, t, ow.mfcc_size)
+        assert n == tn and np.array_equal(m, tm)
+    _, avg = rp.wakeword_template(buf, -1, ow.mfcc_size)
+    assert np.array_equal(avg, ow.avg_features)
+
+
+def test_rpw_reader_rejects_other_files():
+    L = rp.lib()
+    info = api.WakewordInfo()
+    assert L.rp_wakeword_inspect(b"\x00\x01\x02", 3, C.byref(info)) == -3          # RP_ERR_FORMAT
+    assert L.rp_wakeword_inspect(b"", 0, C.byref(info)) == -3
+    # a WakewordModel-shaped map (labels/weights) is outside this path
+    model = bytes([0xA2, 0x66]) + b"labels" + bytes([0x80, 0x67]) + b"weights" + bytes([0xA0])
+    assert L.rp_wakeword_inspect(model, len(model), C.byref(info)) == -4            # RP_ERR_UNSUPPORTED
+    good = open(golden("alexa.rpw"), "rb").read()
+    assert L.rp_wakeword_inspect(good[: len(good) // 2], len(good) // 2, C.byref(info)) == -3  # truncated
+    # options round trip through the oracle's writer (threshold Some / avg None)
+    rng = np.random.default_rng(0)
+    tm = [("a.wav", rng.standard_normal((50, 16)).astype(np.float32)), ("b.wav", rng.standard_normal((60, 16)).astype(np.float32))]
+    buf = O.encode_wakeword("x", tm, avg=None, threshold=0.61, avg_threshold=None, rms_level=0.1)
+    i2 = rp.wakeword_inspect(buf)
+    assert i2["has_threshold"] == 1 and abs(i2["threshold"] - 0.61) < 1e-7 and i2["avg_frames"] == 0 and i2["max_frames"] == 60
+
+
+def _stream_f32():
+    return np.frombuffer(two_wakeword_stream(), dtype="<i2").astype(np.float32) / np.float32(32767.0)
+
+
+def _dense_scores(cfg, rpw, audio):
+    """Oracle per-window scores (no gates) laid out per emitted frame: [n_frames][n_slots]."""
+    ww = O.Wakeword(rpw)
+    T = len(ww.templates)
+    tr = O.trace_window_scores(cfg, rpw, audio, T)  # rows: [avg, aggregate, s_0..s_T-1] per scored window
+    n_frames = audio.size // 160 - 3
+    maxf = max(t.shape[0] for _, t in ww.templates)
+    assert tr.shape[0] == n_frames - maxf + 1
+    has_avg = ww.avg_features is not None
+    dense = np.zeros((n_frames, T + (1 if has_avg else 0)), np.float32)
+    if has_avg:
+        dense[maxf - 1:, 0] = tr[:, 0]
+        dense[maxf - 1:, 1:] = tr[:, 2:]
+    else:
+        dense[maxf - 1:, :] = tr[:, 2:]
+    return dense
+
+
+REPLAY_CASES = [
+    ("oye_casa_g.rpw", dict(score_mode="max")),
+    ("oye_casa_g.rpw", dict(score_mode="median")),
+    ("oye_casa_g.rpw", dict(score_mode="average")),
+    ("oye_casa_g.rpw", dict(score_mode="p90", min_scores=2)),
+    ("oye_casa_g.rpw", dict(score_mode="max", eager=1, min_scores=3)),
+    ("oye_casa_g.rpw", dict(score_mode="max", min_scores=30)),          # partials dropped, never emitted
+    ("oye_casa_g.rpw", dict(score_mode="max", avg_threshold=0.0, threshold=0.3, min_scores=0)),
+    ("oye_casa_g.rpw", dict(score_mode="max", vad_mode="easy")),
+    ("oye_casa_g.rpw", dict(score_mode="max", vad_mode="hard", threshold=0.4)),
+    ("alexa.rpw", dict(score_mode="max", avg_threshold=0.0, threshold=0.45, min_scores=0)),
+    ("alexa.rpw", dict(score_mode="max", avg_threshold=0.0, threshold=0.2, min_scores=1)),
+    ("oye_casa_real.rpw", dict(score_mode="p25", threshold=0.3, avg_threshold=0.1, min_scores=1)),
+]
+
+
+@pytest.mark.parametrize("rpw_name,kw", REPLAY_CASES)
+def test_host_state_machine_matches_oracle_detector(rpw_name, kw):
+    rpw = open(golden(rpw_name), "rb").read()
+    audio = _stream_f32()
+    audio = audio[: audio.size // 480 * 480]
+    cfg_o = O.default_config(**kw)
+    dense = _dense_scores(O.default_config(**{**kw, 'vad_mode': None}), rpw, audio)  # trace scores every window
+    vad = None
+    if kw.get("vad_mode"):
+        mf = O.mfcc_stream(audio, 5)
+        # mean |mfcc| summed in coefficient order, f32 (vad.rs:12)
+        acc = np.zeros(mf.shape[0], np.float32)
+        for k in range(mf.shape[1]):
+            acc = (acc + np.abs(mf[:, k])).astype(np.float32)
+        vad = (acc / np.float32(mf.shape[1])).astype(np.float32)
+    # oracle detector on the same audio
+    det = O.Detector(cfg_o)
+    det.add_wakeword_from_buffer("w", rpw)
+    want = []
+    for c in range(audio.size // 480):
+        d = det.process_samples(audio[480 * c: 480 * (c + 1)])
+        if d is not None:
+            want.append((c, d))
+    got, scored = rp.host_replay(rp.default_config(**kw), [rpw], dense, vad_values=vad)
+    assert scored == det.windows_scored()
+    assert len(got) == len(want), (got, want)
+    for (gc, gd), (wc, wd) in zip(got, want):
+        assert gc == wc
+        assert gd["name"] == wd["name"] and gd["counter"] == wd["counter"]
+        assert gd["score"] == wd["score"] and gd["avg_score"] == wd["avg_score"]
+        assert gd["scores"] == wd["scores"]
+
+
+def test_judgement_modes_match_oracle_aggregate():
+    """score_logic.h percentile/aggregate vs the oracle's (wakeword_comp.rs:38-49,108-139)."""
+    rng = np.random.default_rng(5)
+    for T in (1, 2, 3, 5, 8, 13):
+        tm = [(f"t{i}", rng.standard_normal((4, 16)).astype(np.float32)) for i in range(T)]
+        rpw = O.encode_wakeword("w", tm, avg=None)
+        for mode in O.SCORE_MODES:
+            s = rng.uniform(0.05, 0.7, size=T).astype(np.float32)
+            dense = np.zeros((10, T), np.float32)
+            dense[3] = s  # window ending at frame 3 (4 frames = longest template) is the only hit
+            cfg = rp.default_config(score_mode=mode, threshold=0.0, avg_threshold=0.0, min_scores=0)
+            # countdown = 4/2 = 2 => the partial detection fires two windows later
+            got, _ = rp.host_replay(cfg, [rpw], dense)
+            assert len(got) == 1, mode
+            d = got[0][1]
+            assert d["score"] == O.aggregate(s, mode), (mode, T, d["score"], O.aggregate(s, mode))
+            assert d["counter"] == 1 and d["avg_score"] == 0 and list(d["scores"].values()) == list(s)
