@@ -379,9 +379,10 @@ int rp_batch_last_launches(const rp_batch* b) { return b ? b->core->engine().lau
 // ------------------------------------------------------------------ raw kernels
 int rp_mfcc_frames(const float* audio_dev, int64_t n_streams, int64_t S, int mfcc_size, float* out_dev, void* cuda_stream) {
     return guarded((rp_handle*)nullptr, [&] {
-        if (!audio_dev || !out_dev || n_streams < 1 || mfcc_size < 1 || mfcc_size > kMaxMfccSize) throw Error(RP_ERR_INVALID, "bad argument");
+        if (n_streams < 1 || mfcc_size < 1 || mfcc_size > kMaxMfccSize) throw Error(RP_ERR_INVALID, "bad argument");
         const int64_t hops = S / kHopSamples;
-        if (hops <= 3) return RP_OK;
+        if (hops <= 3) return RP_OK;  // a fresh extractor emits nothing for the first three hops
+        if (!audio_dev || !out_dev) throw Error(RP_ERR_INVALID, "null device pointer");
         int dev = 0;
         cuda_check(cudaGetDevice(&dev), "cudaGetDevice");
         cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
