@@ -162,6 +162,12 @@ int rp_batch_max_mfcc_frames(const rp_batch* b);          /* longest template ov
 int rp_batch_last_timings(const rp_batch* b, float* ms, int cap);
 /* Number of kernels launched by the last rp_batch_process. */
 int rp_batch_last_launches(const rp_batch* b);
+/* Parity-test tap: copies the dense per-window scores of the last rp_batch_process to host memory,
+ * [n_streams][n_new][n_slots] (n_new = samples_per_stream/160 windows, one per new 10 ms hop; slots per
+ * wakeword in insertion order: [avg_features score if present], template 0..T-1). These are the raw
+ * MfccComparator::compare outputs BEFORE the avg gate / threshold; windows the detector would not score
+ * (stream start, after a reset) are present but meaningless. Returns floats written or <0. */
+int64_t rp_batch_copy_last_scores(const rp_batch* b, float* out_host, int64_t cap_floats, int32_t* n_new, int32_t* n_slots);
 
 /* =============================================================================================
  * Raw kernels (micro-benchmarks, parity tests). All pointers are DEVICE pointers.

@@ -84,7 +84,7 @@ EXPORTED = [
     "rp_batch_add_wakeword_from_buffer", "rp_batch_add_wakeword_from_file", "rp_batch_remove_wakewords",
     "rp_batch_set_cuda_stream", "rp_batch_process", "rp_batch_update_config", "rp_batch_reset",
     "rp_batch_windows_scored", "rp_batch_n_streams", "rp_batch_max_mfcc_frames", "rp_batch_last_timings",
-    "rp_batch_last_launches", "rp_mfcc_frames", "rp_dtw_scores", "rp_set_dtw_variant", "rp_wakeword_inspect",
+    "rp_batch_last_launches", "rp_batch_copy_last_scores", "rp_mfcc_frames", "rp_dtw_scores", "rp_set_dtw_variant", "rp_wakeword_inspect",
     "rp_wakeword_template", "rp_host_replay",
 ]
 
@@ -140,6 +140,8 @@ def lib() -> C.CDLL:
     L.rp_batch_max_mfcc_frames.argtypes = [vp]
     L.rp_batch_last_timings.argtypes = [vp, f32p, C.c_int]
     L.rp_batch_last_launches.argtypes = [vp]
+    L.rp_batch_copy_last_scores.restype = C.c_int64
+    L.rp_batch_copy_last_scores.argtypes = [vp, f32p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.rp_mfcc_frames.argtypes = [vp, C.c_int64, C.c_int64, C.c_int, vp, vp]
     L.rp_dtw_scores.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp]
     L.rp_set_dtw_variant.argtypes = [C.c_int]
@@ -325,6 +327,15 @@ class RustpotterBatch:
 
     def last_launches(self) -> int:
         return self._L.rp_batch_last_launches(self._h)
+
+    def last_scores(self, n_new: int, n_slots: int) -> np.ndarray:
+        """Dense [n_streams][n_new][n_slots] window scores of the last process() (parity-test tap)."""
+        out = np.zeros((self.n_streams, n_new, n_slots), np.float32)
+        a, b = C.c_int32(), C.c_int32()
+        n = self._L.rp_batch_copy_last_scores(self._h, out.ctypes.data_as(C.POINTER(C.c_float)), out.size, C.byref(a), C.byref(b))
+        _check(int(n) if n < 0 else 0, self._h)
+        assert (a.value, b.value) == (n_new, n_slots), (a.value, b.value)
+        return out
 
 
 # ---------------------------------------------------------------- raw kernels (torch CUDA tensors)

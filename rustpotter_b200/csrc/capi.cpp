@@ -1,4 +1,5 @@
 // extern "C" surface declared in include/rustpotter_b200.h.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -375,6 +376,21 @@ int rp_batch_last_timings(const rp_batch* b, float* ms, int cap) {
     return n;
 }
 int rp_batch_last_launches(const rp_batch* b) { return b ? b->core->engine().launches : 0; }
+int64_t rp_batch_copy_last_scores(const rp_batch* b, float* out, int64_t cap, int32_t* n_new, int32_t* n_slots) {
+    if (!b || !out) return RP_ERR_INVALID;
+    return guarded(const_cast<rp_batch*>(b), [&]() -> int {
+        const Engine& e = b->core->engine();
+        const int64_t n = e.n_streams() * (int64_t)e.last_n_new() * e.n_slots();
+        if (n_new) *n_new = e.last_n_new();
+        if (n_slots) *n_slots = e.n_slots();
+        if (n > cap) throw Error(RP_ERR_INVALID, "output buffer too small");
+        if (n > 0) {
+            cuda_check(cudaSetDevice(e.device()), "cudaSetDevice");
+            cuda_check(cudaMemcpy(out, e.last_scores_dev(), (size_t)n * sizeof(float), cudaMemcpyDeviceToHost), "D2H scores");
+        }
+        return (int)std::min<int64_t>(n, 0x7fffffff);
+    });
+}
 
 // ------------------------------------------------------------------ raw kernels
 int rp_mfcc_frames(const float* audio_dev, int64_t n_streams, int64_t S, int mfcc_size, float* out_dev, void* cuda_stream) {

@@ -1,0 +1,261 @@
+// K2p — tuned window scorer for the detector pipeline (mfcc_size = 16), sm_100a.
+//
+// Same arithmetic contract as the generic kernel in dtw_kernel.cu (reference
+// src/wakewords/comp/wakeword_comp.rs:22-37 + src/mfcc/{normalizer,comparator,dtw}.rs), restructured
+// around what the detector's workload shares:
+//   * every window of a stream is scored against the SAME templates, and
+//   * consecutive windows of a stream overlap in all but one frame.
+//
+// One CTA scores NW = 128 consecutive windows of one stream against one template ("slot"), one
+// window per thread (plus one helper warp). In the detector n == m, so window = band_size = W and row
+// r touches the 2W columns c in [r-W, r+W-1]. For window j (thread t), column c is frame
+// u = t + c - 1 of the CTA's frame tile, CMN'd with that window's own mean mu_j:
+//     cost(r, c) = 1 - a^_r . (x_u - mu_j) / |x_u - mu_j|          a^_r = a_r / |a_r| (pre-normalised)
+//                = 1 - (G_r[u] - A_r) * inv_c
+//   G_r[u] = a^_r . x_u   is independent of the window -> computed ONCE per (row, frame) and shared
+//                          through shared memory by the 2W windows that need it (the thread that
+//                          has frame u in registers for its own column r+W-1 produces it);
+//   A_r    = a^_r . mu_j  one 16-dim dot per row per window;
+//   inv_c  = 1/|x_u - mu_j| one per column per window, kept in a rotating register file.
+// The DP itself is thread-serial: D[i] (band offset i = c - r + W) is updated in place,
+//     D[i] = cost_i + min3(D[i+1] /*(r-1,c)*/, D[i] /*(r-1,c-1)*/, D[i-1] /*(r,c-1), new*/),
+// 5 instructions per cell (LDS, FADD, FFMA, FMNMX3, FADD) at full lane utilisation, instead of a
+// shuffle wavefront that keeps ~W of 32 lanes busy. 16-dim dots use packed FFMA2/FADD2.
+// The returned cell is D[m-1][n] (dtw.rs:101), i.e. band offset W+1 after row m-1; row m is never
+// computed. Left-border cells (c < 1) stay +inf by induction once row 1 is special-cased; right-
+// border cells (c > m) hold garbage that no valid cell ever reads.
+#include <cfloat>
+#include <cmath>
+
+#include "kernels.h"
+
+namespace rp {
+namespace {
+
+constexpr int kD = 16;
+constexpr int kNW = 128;          // windows (DP threads) per CTA
+constexpr int kThreads = kNW + 32;  // + one helper warp
+constexpr int kXS = 20;           // smem row stride of the frame tile in floats (80 B: LDS.128 conflict-free)
+
+typedef unsigned long long f2;    // packed pair of f32
+
+__device__ __forceinline__ f2 pk(float lo, float hi) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float hsum(f2 v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo + hi;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+    f2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+    f2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float min3(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+struct Row16 {  // 16 floats as 8 packed pairs
+    f2 p[8];
+};
+__device__ __forceinline__ Row16 lds_row(const float* s) {
+    Row16 r;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const float4 v = *reinterpret_cast<const float4*>(s + 4 * q);
+        r.p[2 * q] = pk(v.x, v.y);
+        r.p[2 * q + 1] = pk(v.z, v.w);
+    }
+    return r;
+}
+__device__ __forceinline__ float dot16(const Row16& a, const Row16& b) {
+    f2 acc = fma2(a.p[0], b.p[0], 0ull);
+#pragma unroll
+    for (int q = 1; q < 8; q++) acc = fma2(a.p[q], b.p[q], acc);
+    return hsum(acc);
+}
+
+template <int W>
+__global__ void __launch_bounds__(kThreads) dtw_windows_d16_kernel(DtwWindowsArgs a, const float* __restrict__ tmpl_unit,
+                                                                   int x_rows, int j_blocks) {
+    constexpr int NB = 2 * W;  // band cells per row
+    extern __shared__ __align__(16) float sm[];
+    float* Xs = sm;                              // [x_rows][kXS] frame tile (raw frames)
+    float* Ts = Xs + (size_t)x_rows * kXS;       // [max_len][16] unit template rows
+    float* Gs = Ts + (size_t)a.max_len * kD;     // [2][kNW + NB] shared dot products, double buffered
+    constexpr int GS = kNW + NB;
+
+    const int tid = threadIdx.x;
+    const int64_t cta = blockIdx.x;
+    const int s = (int)(cta % a.n_slots);
+    const int64_t rest = cta / a.n_slots;
+    const int jb = (int)(rest % j_blocks);
+    const int64_t b = rest / j_blocks;
+    const int j0 = jb * kNW;
+    const int m = a.slot_len[s];
+
+    // ---- stage the frame tile and the template in shared memory
+    {
+        const int64_t row0 = (int64_t)a.first_window_row + j0;
+        const float* src = a.frames + (b * a.frame_rows + row0) * kD;
+        const int64_t avail = a.frame_rows - row0;  // rows of this stream from row0 on
+        for (int i = tid; i < x_rows * 4; i += kThreads) {
+            const int u = i >> 2, q = i & 3;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (u < avail) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)u * kD) + q);
+            *reinterpret_cast<float4*>(Xs + u * kXS + 4 * q) = v;
+        }
+        const float4* ts = reinterpret_cast<const float4*>(tmpl_unit + a.slot_off[s]);
+        for (int i = tid; i < m * 4; i += kThreads) reinterpret_cast<float4*>(Ts)[i] = __ldg(ts + i);
+    }
+    __syncthreads();
+
+    const bool dp = tid < kNW;                 // DP thread (one window) vs helper warp
+    const int t = dp ? tid : 0;
+    const bool live = dp && (j0 + tid) < a.n_new;
+
+    // ---- per-window mean (normalizer.rs:3-31: sum over the m frames in order, then / m)
+    f2 nmu[8];  // NEGATED mean, packed
+    {
+        f2 acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc[q] = 0ull;
+        if (dp) {
+            for (int c = 0; c < m; c++) {
+                const Row16 x = lds_row(Xs + (t + c) * kXS);
+#pragma unroll
+                for (int q = 0; q < 8; q++) acc[q] = add2(acc[q], x.p[q]);
+            }
+        }
+        const float fm = (float)m;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            float lo, hi;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[q]));
+            nmu[q] = pk(-__fdiv_rn(lo, fm), -__fdiv_rn(hi, fm));
+        }
+    }
+
+    float D[NB], inv[NB];
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
+        D[i] = INFINITY;
+        inv[i] = 0.f;
+    }
+    D[W] = 0.f;  // D[0][0] seen from row 1 as its (r-1, c-1) neighbour of column 1
+
+    // columns 1 .. W-1 enter the band before row 1 (column r+W-1 enters at row r)
+    auto col_inv = [&](int u) -> float {  // 1 / |x_u - mu|, 0 when the vector is 0 (similarity 0)
+        const Row16 x = lds_row(Xs + u * kXS);
+        f2 nn = 0ull;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const f2 y = add2(x.p[q], nmu[q]);
+            nn = fma2(y, y, nn);
+        }
+        const float n2 = hsum(nn);
+        return n2 > 0.f ? rsqrtf(n2) : 0.f;
+    };
+    if (dp) {
+#pragma unroll
+        for (int c = 1; c < W; c++) inv[c % NB] = col_inv(t + c - 1);
+    }
+
+    const int last_row = m - 1;  // rows 1 .. m-1 (the result lives in row m-1)
+    for (int r0 = 0; r0 < last_row; r0 += NB) {
+#pragma unroll
+        for (int k = 0; k < NB; k++) {
+            const int r = r0 + k + 1;  // r % NB == (k + 1) % NB because r0 is a multiple of NB
+            if (r <= last_row) {       // uniform over the CTA
+                float* G = Gs + (r & 1) * GS;
+                const Row16 ar = lds_row(Ts + (r - 1) * kD);  // broadcast
+                float A = 0.f;
+                if (dp) {
+                    // own new column c = r+W-1 <-> frame u = t + r + W - 2
+                    const int u = t + r + W - 2;
+                    const Row16 x = lds_row(Xs + u * kXS);
+                    f2 nn = 0ull, g = 0ull, aa = 0ull;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const f2 y = add2(x.p[q], nmu[q]);
+                        nn = fma2(y, y, nn);
+                        g = fma2(ar.p[q], x.p[q], g);
+                        aa = fma2(ar.p[q], nmu[q], aa);
+                    }
+                    const float n2 = hsum(nn);
+                    inv[(k + W) % NB] = n2 > 0.f ? rsqrtf(n2) : 0.f;  // column r+W-1 = (k+1)+W-1 mod NB
+                    G[t + NB - 1] = hsum(g);
+                    A = -hsum(aa);                                     // a^_r . mu  (nmu is negated)
+                } else if (tid - kNW < NB - 1) {
+                    // helper warp: the NB-1 lowest frames of this row's shared range
+                    const int e = tid - kNW;
+                    const int u = r - W - 1 + e;
+                    float g = 0.f;
+                    if (u >= 0) {
+                        const Row16 x = lds_row(Xs + u * kXS);
+                        g = dot16(ar, x);
+                    }
+                    G[e] = g;
+                }
+                __syncthreads();
+                if (dp) {
+                    if (r == 1) {
+                        // row 1: columns c < 1 must stay +inf (they would otherwise inherit D[0][0])
+#pragma unroll
+                        for (int i = W; i < NB; i++) {
+                            const float sim = (G[t + i] - A) * inv[(k + i + 1 + NB - W) % NB];
+                            const float best = min3(i + 1 < NB ? D[i + 1] : INFINITY, D[i], D[i - 1]);
+                            D[i] = (1.f - sim) + best;
+                        }
+                        D[W - 1] = INFINITY;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < NB; i++) {
+                            // column c = r - W + i  ->  inv slot c % NB = (k + 1 - W + i) mod NB
+                            const float sim = (G[t + i] - A) * inv[(k + i + 1 + NB - W) % NB];
+                            const float best = min3(i + 1 < NB ? D[i + 1] : INFINITY, D[i], i > 0 ? D[i - 1] : INFINITY);
+                            D[i] = (1.f - sim) + best;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (live) {
+        // D[m-1][m] = band offset W+1 of row m-1 (dtw.rs:101); m == 1 has no such cell -> +inf
+        const float cost = m >= 2 ? D[W + 1] : INFINITY;
+        const float normalized = __fdiv_rn(cost, (float)(2 * m));
+        const float score = __fdiv_rn(1.f, 1.f + expf(__fdiv_rn(normalized - a.score_ref, a.score_ref)));
+        a.scores[(b * a.n_new + (j0 + tid)) * a.n_slots + s] = score;
+    }
+}
+
+}  // namespace
+
+// Unit-normalised templates are prepared by the engine (tmpl_unit has the layout of a.tmpl).
+cudaError_t launch_dtw_windows_d16(const DtwWindowsArgs& a, const float* tmpl_unit, cudaStream_t stream) {
+    if (a.d != kD || a.band != 5) return cudaErrorInvalidValue;
+    constexpr int W = 5;
+    const int j_blocks = (a.n_new + kNW - 1) / kNW;
+    const int64_t ctas = a.n_streams * (int64_t)j_blocks * a.n_slots;
+    if (ctas <= 0) return cudaSuccess;
+    if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
+    const int x_rows = kNW + a.max_len + W;
+    const size_t bytes = ((size_t)x_rows * kXS + (size_t)a.max_len * kD + 2 * (kNW + 2 * W)) * sizeof(float);
+    if (bytes > 200 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(dtw_windows_d16_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    dtw_windows_d16_kernel<W><<<(unsigned)ctas, kThreads, bytes, stream>>>(a, tmpl_unit, x_rows, j_blocks);
+    return cudaGetLastError();
+}
+
+}  // namespace rp

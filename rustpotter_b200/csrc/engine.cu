@@ -1,6 +1,7 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 namespace rp {
@@ -98,6 +99,16 @@ void Engine::configure(const WakewordSet& ws, const rp_config& cfg) {
         tmpl.insert(tmpl.end(), m.v.begin(), m.v.end());
     }
     upload(tmpl_, tmpl, stream_, "templates");
+    {   // unit-length rows for the tuned kernels: a / sqrt(|a|^2), zero rows stay zero
+        std::vector<float> unit(tmpl.size());
+        for (size_t r = 0; r + d_ <= tmpl.size(); r += (size_t)d_) {
+            float n2 = 0.f;
+            for (int k = 0; k < d_; k++) n2 += tmpl[r + k] * tmpl[r + k];
+            const float inv = n2 > 0.f ? 1.f / std::sqrt(n2) : 0.f;
+            for (int k = 0; k < d_; k++) unit[r + k] = tmpl[r + k] * inv;
+        }
+        upload(tmpl_unit_, unit, stream_, "unit templates");
+    }
     upload(slot_off_, off, stream_, "slot offsets");
     upload(slot_len_, len, stream_, "slot lengths");
     upload(metas_, ws.metas, stream_, "wakeword metas");
@@ -219,7 +230,10 @@ void Engine::process(const float* audio, int64_t S, bool on_device, bool want_va
     wa.band = band_;
     wa.score_ref = score_ref_;
     wa.scores = tscore_.as<float>();
-    cuda_check(launch_dtw_windows_generic(wa, stream_), "dtw kernel");
+    if (d_ == 16 && band_ == 5 && dtw_variant_ != 1)
+        cuda_check(launch_dtw_windows_d16(wa, tmpl_unit_.as<float>(), stream_), "dtw window kernel");
+    else
+        cuda_check(launch_dtw_windows_generic(wa, stream_), "dtw kernel");
     JudgeArgs ja;
     ja.scores = tscore_.as<float>();
     ja.n_streams = n_streams_;

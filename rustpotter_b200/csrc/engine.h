@@ -70,6 +70,7 @@ class Engine {
     const float* last_scores_dev() const { return tscore_.as<float>(); }
     const float* last_frames_dev(int64_t* rows_per_stream, int* first_new_row) const;
     int n_slots() const { return n_slots_; }
+    int last_n_new() const { return last_n_new_; }
 
   private:
     void ensure_frames(int n_new);
@@ -84,7 +85,7 @@ class Engine {
     int d_ = 0, max_frames_ = 0, n_slots_ = 0, n_wakewords_ = 0, max_templates_ = 0, max_slot_len_ = 0;
     int band_ = 5, score_mode_ = 1;
     float score_ref_ = 0.22f;
-    DeviceBuffer tmpl_, slot_off_, slot_len_, metas_;
+    DeviceBuffer tmpl_, tmpl_unit_, slot_off_, slot_len_, metas_;
     // MFCC tables on device
     DeviceBuffer hamming_, tw480_, mel_bank_, centres_, dct_;
     MfccTablesDev tables_;

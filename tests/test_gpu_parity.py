@@ -328,3 +328,34 @@ def test_batch_two_wakewords_and_device_audio():
     assert sorted((s, d["name"], d["counter"]) for s, c, d in got) == sorted(
         (b, w["name"], w["counter"]) for b in range(5) for w in want[b])
     assert len(got) >= 3 and bt.windows_scored() == total
+
+
+# ------------------------------------------------------------------ tuned window kernel vs generic kernel vs oracle
+@pytest.mark.parametrize("lengths", [(88, 92, 96, 100, 100, 96, 92, 100), (40, 57, 33), (150, 131, 144, 150)])
+def test_window_scores_tuned_vs_generic_vs_oracle(lengths):
+    """Dense per-window scores: the tuned d=16 kernel against the reference-order generic kernel and
+    the oracle's per-window trace (same audio, every window, every template, avg included)."""
+    rpw, utts = make_wakeword(O, d=16, lengths=lengths, seed=77)
+    n_chunks = 160
+    audio = synth_audio(3, n_chunks * 480, seed=5)
+    splice(audio[0], utts[0], 120)
+    splice(audio[2], utts[-1], 33)
+    audio[1, 20000:30000] *= np.float32(0.01)          # a quiet stretch (large |mean| / |deviation| ratio)
+    T, maxf = len(lengths), max(lengths)
+    res = {}
+    for variant in (1, 2):
+        rp.set_dtw_variant(variant)
+        bt = rp.RustpotterBatch(3)
+        bt.add_wakeword_from_buffer("w", rpw)
+        bt.process(audio)
+        res[variant] = bt.last_scores(n_chunks * 3, T + 1)
+    rp.set_dtw_variant(0)
+    first = maxf + 2                                    # hop of the first window a fresh detector scores
+    for b in range(3):
+        tr = O.trace_window_scores(O.default_config(), rpw, audio[b], T)   # [avg, agg, s...]
+        want = np.concatenate([tr[:, :1], tr[:, 2:]], axis=1)
+        for variant, tol in ((1, 5e-6), (2, SCORE_RTOL)):
+            got = res[variant][b, first:]
+            assert got.shape == want.shape
+            rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-12)
+            assert rel.max() < tol, (lengths, b, variant, rel.max(), np.unravel_index(rel.argmax(), rel.shape))
