@@ -168,7 +168,7 @@ __global__ void judge_windows_kernel(JudgeArgs a) {
         if (idx >= a.capacity) continue;
         float* rec = a.hits + (int64_t)idx * stride;
         const WakewordMeta m = a.metas[jd.wakeword];
-        rec[0] = __int_as_float((int)(w / a.n_new));
+        rec[0] = __int_as_float(a.stream_base + (int)(w / a.n_new));
         rec[1] = __int_as_float((int)(w % a.n_new));
         rec[2] = __int_as_float(jd.wakeword);
         rec[3] = jd.avg_score;

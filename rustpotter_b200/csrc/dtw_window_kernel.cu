@@ -93,6 +93,10 @@ __global__ void __launch_bounds__(kThreads) dtw_windows_d16_kernel(DtwWindowsArg
     float* Ts = Xs + (size_t)x_rows * kXS;       // [max_len][16] unit template rows
     float* Gs = Ts + (size_t)a.max_len * kD;     // [2][kNW + NB] shared dot products, double buffered
     constexpr int GS = kNW + NB;
+    float* Os = Gs + 2 * GS;                     // [kThreads/16 + 1][16] segment offsets of the row prefix (16 B aligned)
+    const int p_rows = kNW + a.max_len + 1;      // prefix rows 0 .. kNW + m
+    const int SEG = (p_rows + kThreads / 16 - 1) / (kThreads / 16);  // rows per prefix segment
+    float* Ps = Os + (kThreads / 16 + 1) * kD;   // [p_rows][kXS] exclusive row prefix sums within SEG-row segments
 
     const int tid = threadIdx.x;
     const int64_t cta = blockIdx.x;
@@ -123,25 +127,48 @@ __global__ void __launch_bounds__(kThreads) dtw_windows_d16_kernel(DtwWindowsArg
     const int t = dp ? tid : 0;
     const bool live = dp && (j0 + tid) < a.n_new;
 
-    // ---- per-window mean (normalizer.rs:3-31: sum over the m frames in order, then / m)
-    f2 nmu[8];  // NEGATED mean, packed
+    // ---- per-window mean (normalizer.rs:3-31) from a cooperative prefix sum over the tile rows:
+    // Ps[u] = sum of rows < u within the SEG-row segment of u, Os[seg] = sum of all earlier segments;
+    // window sum of thread t = P(t+m) - P(t). (Reading the m frames per thread instead costs a third
+    // of the kernel's shared-memory bandwidth; the prefix form differs from the reference's
+    // sequential sum by O(1e-6) relative, far inside the parity bar.)
     {
-        f2 acc[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) acc[q] = 0ull;
-        if (dp) {
-            for (int c = 0; c < m; c++) {
-                const Row16 x = lds_row(Xs + (t + c) * kXS);
-#pragma unroll
-                for (int q = 0; q < 8; q++) acc[q] = add2(acc[q], x.p[q]);
+        const int seg = tid >> 4, dd = tid & 15;  // 160 threads = 10 segments x 16 coefficients
+        float run = 0.f;
+        for (int i = 0; i < SEG; i++) {
+            const int u = seg * SEG + i;
+            if (u < p_rows) {
+                Ps[u * kXS + dd] = run;
+                if (u < x_rows) run += Xs[u * kXS + dd];
             }
         }
+        Os[(seg + 1) * kD + dd] = run;
+        __syncthreads();
+        if (tid < kD) {
+            float acc = 0.f;
+            Os[tid] = 0.f;
+            for (int g = 1; g <= kThreads / 16; g++) {
+                acc += Os[g * kD + tid];
+                Os[g * kD + tid] = acc;
+            }
+        }
+        __syncthreads();
+    }
+    f2 nmu[8];  // NEGATED mean, packed
+    {
+        const int u0 = t, u1 = t + m;
+        const Row16 p0 = lds_row(Ps + u0 * kXS), p1 = lds_row(Ps + u1 * kXS);
+        const Row16 o0 = lds_row(Os + (u0 / SEG) * kD), o1 = lds_row(Os + (u1 / SEG) * kD);
         const float fm = (float)m;
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-            float lo, hi;
-            asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[q]));
-            nmu[q] = pk(-__fdiv_rn(lo, fm), -__fdiv_rn(hi, fm));
+            float a0, a1, b0, b1, c0, c1, d0, d1;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(p1.p[q]));
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(b0), "=f"(b1) : "l"(p0.p[q]));
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(o1.p[q]));
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(o0.p[q]));
+            const float s0 = (a0 - b0) + (c0 - d0), s1 = (a1 - b1) + (c1 - d1);
+            nmu[q] = pk(-__fdiv_rn(s0, fm), -__fdiv_rn(s1, fm));
         }
     }
 
@@ -250,7 +277,9 @@ cudaError_t launch_dtw_windows_d16(const DtwWindowsArgs& a, const float* tmpl_un
     if (ctas <= 0) return cudaSuccess;
     if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
     const int x_rows = kNW + a.max_len + W;
-    const size_t bytes = ((size_t)x_rows * kXS + (size_t)a.max_len * kD + 2 * (kNW + 2 * W)) * sizeof(float);
+    const int p_rows = kNW + a.max_len + 1;
+    const size_t bytes = ((size_t)x_rows * kXS + (size_t)a.max_len * kD + 2 * (kNW + 2 * W) + (kThreads / 16 + 1) * kD +
+                          (size_t)p_rows * kXS) * sizeof(float);
     if (bytes > 200 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(dtw_windows_d16_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;

@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace rp {
@@ -42,6 +43,8 @@ Engine::Engine(int device, int64_t n_streams) : device_(device), n_streams_(n_st
     cuda_check(cudaSetDevice(device_), "cudaSetDevice");
     cuda_check(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking), "cudaStreamCreate");
     stream_ = own_stream_;
+    cuda_check(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (const char* g = std::getenv("RP_GROUP_STREAMS")) group_streams_ = std::max(1, std::atoi(g));
     for (auto& ev : ev_) cuda_check(cudaEventCreate(&ev), "cudaEventCreate");
     carry_.reserve((size_t)n_streams_ * 2 * kHopSamples * sizeof(float), "carry");
     cuda_check(cudaMemsetAsync(carry_.as<void>(), 0, carry_.bytes(), stream_), "memset carry");
@@ -54,6 +57,9 @@ Engine::~Engine() {
     if (own_stream_) cudaStreamSynchronize(own_stream_);
     for (auto& ev : ev_)
         if (ev) cudaEventDestroy(ev);
+    for (auto& ev : group_ev_)
+        if (ev) cudaEventDestroy(ev);
+    if (copy_stream_) cudaStreamDestroy(copy_stream_);
     if (hit_host_) cudaFreeHost(hit_host_);
     if (count_host_) cudaFreeHost(count_host_);
     if (own_stream_) cudaStreamDestroy(own_stream_);
@@ -184,75 +190,95 @@ void Engine::process(const float* audio, int64_t S, bool on_device, bool want_va
     ensure_frames(n_new);
     launches = 0;
     const int64_t rows = (int64_t)hist_ + frames_cap_;
-    const size_t audio_bytes = (size_t)n_streams_ * S * sizeof(float);
-
-    cuda_check(cudaEventRecord(ev_[0], stream_), "event");
-    const float* src = audio;
-    if (!on_device) {
-        audio_.reserve(audio_bytes, "audio staging");
-        cuda_check(cudaMemcpyAsync(audio_.as<void>(), audio, audio_bytes, cudaMemcpyHostToDevice, stream_), "H2D audio");
-        src = audio_.as<float>();
-    }
-    cuda_check(cudaEventRecord(ev_[1], stream_), "event");
-
-    // K1: frame j of this call ends at new hop j and starts two hops earlier (carry or earlier audio)
+    const int64_t n_windows = n_streams_ * (int64_t)n_new;
+    const int stride = 5 + max_templates_;
+    tscore_.reserve((size_t)n_windows * n_slots_ * sizeof(float), "window scores");
+    hits_.reserve((size_t)n_windows * stride * sizeof(float), "hit list");
     float* vad_dev = nullptr;
     if (want_vad) {
-        vad_.reserve((size_t)n_streams_ * n_new * sizeof(float), "vad values");
+        vad_.reserve((size_t)n_windows * sizeof(float), "vad values");
         vad_dev = vad_.as<float>();
     }
-    float* fb = frames_[cur_].as<float>();
-    cuda_check(launch_mfcc_frames(src, S, carry_.as<float>(), n_streams_, n_new, -2 * kHopSamples, tables_, fb, rows, hist_,
-                                  vad_dev, stream_), "mfcc kernel");
-    cuda_check(launch_copy_rows(src + (S - 2 * kHopSamples), S, carry_.as<float>(), 2 * kHopSamples, n_streams_,
-                                2 * kHopSamples, stream_), "carry update");
-    launches += 2;
-    cuda_check(cudaEventRecord(ev_[2], stream_), "event");
+    if (!on_device) audio_.reserve((size_t)n_streams_ * S * sizeof(float), "audio staging");
+    const float* src_all = on_device ? audio : audio_.as<float>();
 
-    // K2: window scores; K3: judgement -> compact hit list
-    const int64_t n_windows = n_streams_ * (int64_t)n_new;
-    tscore_.reserve((size_t)n_windows * n_slots_ * sizeof(float), "window scores");
-    const int stride = 5 + max_templates_;
-    hits_.reserve((size_t)n_windows * stride * sizeof(float), "hit list");
+    // The batch is processed in groups of streams: group g's kernels wait only for group g's H2D copy,
+    // so the copy of group g+1 (copy stream) overlaps the kernels of group g, and a group's frames
+    // (~33 MB for 512 streams x 10 s) are still in L2 when its DTW kernel reads them.
+    const int64_t gs = std::min<int64_t>(group_streams_, n_streams_);
+    const int n_groups = (int)((n_streams_ + gs - 1) / gs);
+    while ((int)group_ev_.size() < 4 * n_groups) {
+        cudaEvent_t ev;
+        cuda_check(cudaEventCreate(&ev), "cudaEventCreate");
+        group_ev_.push_back(ev);
+    }
+    cuda_check(cudaEventRecord(ev_[0], stream_), "event");
+    if (!on_device) {
+        cuda_check(cudaStreamWaitEvent(copy_stream_, ev_[0], 0), "wait");
+        for (int g = 0; g < n_groups; g++) {
+            const int64_t b0 = g * gs, nb = std::min(gs, n_streams_ - b0);
+            cuda_check(cudaMemcpyAsync(audio_.as<float>() + b0 * S, audio + b0 * S, (size_t)nb * S * sizeof(float),
+                                       cudaMemcpyHostToDevice, copy_stream_), "H2D audio");
+            cuda_check(cudaEventRecord(group_ev_[4 * g], copy_stream_), "event");
+        }
+    }
     cuda_check(cudaMemsetAsync(hit_count_.as<void>(), 0, sizeof(int), stream_), "memset");
-    DtwWindowsArgs wa;
-    wa.frames = fb;
-    wa.frame_rows = rows;
-    wa.first_window_row = hist_ - (max_frames_ - 1);
-    wa.n_new = n_new;
-    wa.n_streams = n_streams_;
-    wa.d = d_;
-    wa.tmpl = tmpl_.as<float>();
-    wa.slot_off = slot_off_.as<int64_t>();
-    wa.slot_len = slot_len_.as<int32_t>();
-    wa.n_slots = n_slots_;
-    wa.max_len = max_slot_len_;
-    wa.band = band_;
-    wa.score_ref = score_ref_;
-    wa.scores = tscore_.as<float>();
-    if (d_ == 16 && band_ == 5 && dtw_variant_ != 1)
-        cuda_check(launch_dtw_windows_d16(wa, tmpl_unit_.as<float>(), stream_), "dtw window kernel");
-    else
-        cuda_check(launch_dtw_windows_generic(wa, stream_), "dtw kernel");
-    JudgeArgs ja;
-    ja.scores = tscore_.as<float>();
-    ja.n_streams = n_streams_;
-    ja.n_new = n_new;
-    ja.n_slots = n_slots_;
-    ja.metas = metas_.as<WakewordMeta>();
-    ja.n_wakewords = n_wakewords_;
-    ja.score_mode = score_mode_;
-    ja.max_templates = max_templates_;
-    ja.hit_count = hit_count_.as<int>();
-    ja.hits = hits_.as<float>();
-    ja.capacity = n_windows;
-    cuda_check(launch_judge_windows(ja, stream_), "judge kernel");
-    // next call's history = the last hist_ rows of [history | new frames]
-    if (hist_ > 0)
-        cuda_check(launch_copy_rows(fb + (size_t)n_new * d_, rows * d_, frames_[1 - cur_].as<float>(), rows * d_, n_streams_,
-                                    (int64_t)hist_ * d_, stream_), "history move");
+    float* fb_all = frames_[cur_].as<float>();
+    for (int g = 0; g < n_groups; g++) {
+        const int64_t b0 = g * gs, nb = std::min(gs, n_streams_ - b0);
+        if (!on_device) cuda_check(cudaStreamWaitEvent(stream_, group_ev_[4 * g], 0), "wait");
+        cuda_check(cudaEventRecord(group_ev_[4 * g + 1], stream_), "event");
+        const float* src = src_all + b0 * S;
+        float* fb = fb_all + b0 * rows * d_;
+        float* carry = carry_.as<float>() + b0 * 2 * kHopSamples;
+        // K1: frame j of this call ends at new hop j and starts two hops earlier (carry or earlier audio)
+        cuda_check(launch_mfcc_frames(src, S, carry, nb, n_new, -2 * kHopSamples, tables_, fb, rows, hist_,
+                                      vad_dev ? vad_dev + b0 * n_new : nullptr, stream_), "mfcc kernel");
+        cuda_check(launch_copy_rows(src + (S - 2 * kHopSamples), S, carry, 2 * kHopSamples, nb, 2 * kHopSamples, stream_),
+                   "carry update");
+        cuda_check(cudaEventRecord(group_ev_[4 * g + 2], stream_), "event");
+        // K2: window scores; K3: judgement -> compact hit list
+        DtwWindowsArgs wa;
+        wa.frames = fb;
+        wa.frame_rows = rows;
+        wa.first_window_row = hist_ - (max_frames_ - 1);
+        wa.n_new = n_new;
+        wa.n_streams = nb;
+        wa.d = d_;
+        wa.tmpl = tmpl_.as<float>();
+        wa.slot_off = slot_off_.as<int64_t>();
+        wa.slot_len = slot_len_.as<int32_t>();
+        wa.n_slots = n_slots_;
+        wa.max_len = max_slot_len_;
+        wa.band = band_;
+        wa.score_ref = score_ref_;
+        wa.scores = tscore_.as<float>() + b0 * (int64_t)n_new * n_slots_;
+        if (d_ == 16 && band_ == 5 && dtw_variant_ != 1)
+            cuda_check(launch_dtw_windows_d16(wa, tmpl_unit_.as<float>(), stream_), "dtw window kernel");
+        else
+            cuda_check(launch_dtw_windows_generic(wa, stream_), "dtw kernel");
+        JudgeArgs ja;
+        ja.scores = wa.scores;
+        ja.n_streams = nb;
+        ja.n_new = n_new;
+        ja.n_slots = n_slots_;
+        ja.metas = metas_.as<WakewordMeta>();
+        ja.n_wakewords = n_wakewords_;
+        ja.score_mode = score_mode_;
+        ja.max_templates = max_templates_;
+        ja.hit_count = hit_count_.as<int>();
+        ja.hits = hits_.as<float>();
+        ja.capacity = n_windows;
+        ja.stream_base = (int)b0;
+        cuda_check(launch_judge_windows(ja, stream_), "judge kernel");
+        // next call's history = the last hist_ rows of [history | new frames]
+        if (hist_ > 0)
+            cuda_check(launch_copy_rows(fb + (size_t)n_new * d_, rows * d_, frames_[1 - cur_].as<float>() + b0 * rows * d_,
+                                        rows * d_, nb, (int64_t)hist_ * d_, stream_), "history move");
+        cuda_check(cudaEventRecord(group_ev_[4 * g + 3], stream_), "event");
+        launches += 5;
+    }
     cur_ ^= 1;
-    launches += 3;
     last_n_new_ = n_new;
     cuda_check(cudaEventRecord(ev_[3], stream_), "event");
 
@@ -277,7 +303,18 @@ void Engine::process(const float* audio, int64_t S, bool on_device, bool want_va
     }
     cuda_check(cudaEventRecord(ev_[4], stream_), "event");
     cuda_check(cudaStreamSynchronize(stream_), "sync");
-    for (int i = 0; i < 4; i++) cudaEventElapsedTime(&timings_ms[i], ev_[i], ev_[i + 1]);
+    // stage times: [0] H2D (first copy start .. last copy end; overlaps the kernels), [1] MFCC and
+    // [2] DTW + judge summed over groups, [3] D2H of the hit list
+    timings_ms[0] = timings_ms[1] = timings_ms[2] = 0.f;
+    if (!on_device) cudaEventElapsedTime(&timings_ms[0], ev_[0], group_ev_[4 * (n_groups - 1)]);
+    for (int g = 0; g < n_groups; g++) {
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, group_ev_[4 * g + 1], group_ev_[4 * g + 2]);
+        cudaEventElapsedTime(&b, group_ev_[4 * g + 2], group_ev_[4 * g + 3]);
+        timings_ms[1] += a;
+        timings_ms[2] += b;
+    }
+    cudaEventElapsedTime(&timings_ms[3], ev_[3], ev_[4]);
 
     hits.resize((size_t)n_hits);
     for (int i = 0; i < n_hits; i++) {

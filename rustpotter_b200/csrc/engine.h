@@ -77,8 +77,10 @@ class Engine {
 
     int device_ = 0;
     int64_t n_streams_ = 0;
-    cudaStream_t stream_ = nullptr, own_stream_ = nullptr;
+    cudaStream_t stream_ = nullptr, own_stream_ = nullptr, copy_stream_ = nullptr;
     cudaEvent_t ev_[6] = {};
+    std::vector<cudaEvent_t> group_ev_;   // [group][4]: copy done, start, after MFCC, after DTW/judge
+    int group_streams_ = 256;             // streams per pipeline group (RP_GROUP_STREAMS)
     int dtw_variant_ = 0;
 
     // wakeword set on device

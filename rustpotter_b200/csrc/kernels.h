@@ -85,6 +85,7 @@ struct JudgeArgs {
     int* hit_count = nullptr;          // device counter (zeroed by the caller)
     float* hits = nullptr;             // device [capacity][5 + max_templates]
     int64_t capacity = 0;
+    int stream_base = 0;               // added to the stream index written into hit records (group offset)
 };
 cudaError_t launch_judge_windows(const JudgeArgs& a, cudaStream_t stream);
 

@@ -359,3 +359,19 @@ def test_window_scores_tuned_vs_generic_vs_oracle(lengths):
             assert got.shape == want.shape
             rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-12)
             assert rel.max() < tol, (lengths, b, variant, rel.max(), np.unravel_index(rel.argmax(), rel.shape))
+
+
+def test_batch_stream_groups_do_not_change_results(monkeypatch):
+    """The engine pipelines the batch in groups of streams (H2D of group g+1 under the kernels of
+    group g); results must not depend on the group size. Host (pinned and pageable) and device audio."""
+    torch = _torch()
+    rpw, audio, _ = _batch_case(B=10, n_chunks=120)
+    outs = []
+    for group, src in ((512, "host"), (4, "host"), (3, "pinned"), (4, "device"), (1, "host")):
+        monkeypatch.setenv("RP_GROUP_STREAMS", str(group))
+        bt = rp.RustpotterBatch(10)
+        bt.add_wakeword_from_buffer("w0", rpw)
+        a = audio if src == "host" else torch.from_numpy(audio).pin_memory() if src == "pinned" else torch.from_numpy(audio).cuda()
+        got = bt.process(a)
+        outs.append((sorted((s, c, d["counter"], float(d["score"]), float(d["avg_score"])) for s, c, d in got), bt.windows_scored()))
+    assert outs[0][0] and all(o == outs[0] for o in outs[1:])
