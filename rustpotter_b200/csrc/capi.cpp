@@ -431,7 +431,10 @@ int rp_dtw_scores(const float* tmpl_dev, const int64_t* tmpl_off_dev, const int3
         a.score_ref = score_ref;
         a.cmn = cmn;
         a.out = out_dev;
-        cuda_check(launch_dtw_pairs_generic(a, static_cast<cudaStream_t>(cuda_stream)), "dtw kernel");
+        if (g_dtw_variant != 1 && dtw_pairs_stream_supported(a))
+            cuda_check(launch_dtw_pairs_stream(a, static_cast<cudaStream_t>(cuda_stream)), "dtw stream kernel");
+        else
+            cuda_check(launch_dtw_pairs_generic(a, static_cast<cudaStream_t>(cuda_stream)), "dtw kernel");
         return RP_OK;
     });
 }

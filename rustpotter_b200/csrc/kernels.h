@@ -47,6 +47,10 @@ struct DtwPairsArgs {
 };
 // K2 generic ("faithful") kernel: one warp per pair, anti-diagonal wavefront, reference operation order.
 cudaError_t launch_dtw_pairs_generic(const DtwPairsArgs& a, cudaStream_t stream);
+// K2s streaming kernel for independent pairs (dtw_stream_kernel.cu): d == 16, uniform lengths, no CMN,
+// window = max(band, |m-n|) <= 23.
+bool dtw_pairs_stream_supported(const DtwPairsArgs& a);
+cudaError_t launch_dtw_pairs_stream(const DtwPairsArgs& a, cudaStream_t stream);
 
 // Pipeline scoring: every new frame j of every stream closes a window; slot s scores the first
 // slot_len[s] frames of that window (after CMN) against template s.

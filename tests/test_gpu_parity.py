@@ -74,6 +74,9 @@ def _rel(a, b):
     (100, 100, 16, 5, True), (120, 100, 16, 5, False), (100, 120, 16, 5, False), (93, 93, 5, 5, True),
     (108, 108, 5, 2, True), (50, 50, 16, 1, False), (64, 70, 13, 9, True), (30, 30, 16, 40, False),
     (3, 3, 16, 5, True), (1, 1, 16, 5, False), (2, 1, 4, 5, False), (168, 168, 5, 5, True), (100, 100, 31, 5, True),
+    # shapes that take the streaming kernel (d = 16, no CMN, window <= 23)
+    (100, 100, 16, 5, False), (100, 100, 16, 20, False), (64, 72, 16, 9, False), (119, 97, 16, 5, False), (16, 8, 16, 5, False),
+    (2, 2, 16, 5, False), (60, 7, 16, 60, False), (128, 105, 16, 23, False), (200, 192, 16, 11, False), (45, 50, 16, 2, False),
 ])
 def test_dtw_kernel_matches_oracle(m, n, d, band, cmn):
     torch = _torch()
@@ -87,14 +90,39 @@ def test_dtw_kernel_matches_oracle(m, n, d, band, cmn):
         w[1] = a[1]
     a[2, m // 2] = 0.0                            # zero vector inside a template (similarity 0 rule)
     w[3, :] = 0.0                                 # all-zero window
-    got = rp.dtw_scores(torch.from_numpy(a).cuda(), torch.from_numpy(w).cuda(), band=band, cmn=cmn).cpu().numpy()
+    ref = []
     for p in range(P):
         wb = O.normalize(w[p]) if cmn else w[p]
-        ref = O.compare(a[p], wb, band, 0.22)
-        if ref == 0.0:
-            assert got[p] == 0.0, (p, got[p])
-        else:
-            assert _rel(got[p], ref) < 5e-6, (p, got[p], ref)
+        ref.append(O.compare(a[p], wb, band, 0.22))
+    # variant 1 = generic kernel (reference operation order, held to 5e-6); 0 = automatic choice
+    # (streaming kernel where it applies; FFMA2 dots + rsqrt change the rounding, held to 3e-5)
+    for variant, tol in ((1, 5e-6), (0, 3e-5)):
+        rp.set_dtw_variant(variant)
+        got = rp.dtw_scores(torch.from_numpy(a).cuda(), torch.from_numpy(w).cuda(), band=band, cmn=cmn).cpu().numpy()
+        rp.set_dtw_variant(0)
+        for p in range(P):
+            if ref[p] == 0.0:
+                assert got[p] == 0.0, (variant, p, got[p])
+            else:
+                assert _rel(got[p], ref[p]) < tol, (variant, p, got[p], ref[p])
+
+
+def test_dtw_stream_kernel_many_pairs_vs_generic():
+    """The streaming kernel against the reference-order generic kernel on BASELINE configs[3]'s shape,
+    enough pairs to fill every SM several times (partial last group included)."""
+    torch = _torch()
+    P = 148 * 9 * 5 * 3 + 3
+    g = torch.Generator(device="cuda").manual_seed(99)
+    scale = torch.tensor([8, 4, 3, 2, 2, 1.5] + [1.0] * 10, device="cuda")
+    a = torch.randn((P, 120, 16), device="cuda", generator=g) * scale
+    w = torch.randn((P, 100, 16), device="cuda", generator=g) * scale
+    rp.set_dtw_variant(1)
+    ref = rp.dtw_scores(a, w, band=5)
+    rp.set_dtw_variant(0)
+    got = rp.dtw_scores(a, w, band=5)
+    rel = ((got - ref).abs() / ref.abs().clamp_min(1e-12)).max().item()
+    assert rel < 3e-5, rel
+    assert float(ref.min()) > 0
 
 
 def test_dtw_ragged_pairs():
