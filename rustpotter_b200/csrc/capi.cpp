@@ -440,7 +440,9 @@ int rp_dtw_scores(const float* tmpl_dev, const int64_t* tmpl_off_dev, const int3
 }
 
 int rp_set_dtw_variant(int v) {
-    g_dtw_variant = v;
+    // 0 automatic, 1 generic kernel, 2 tuned kernels, 3 tuned with the one-row-per-step streaming kernel
+    g_dtw_variant = v == 3 ? 2 : v;
+    set_dtw_stream_rows(v == 3 ? 1 : 0);
     return RP_OK;
 }
 

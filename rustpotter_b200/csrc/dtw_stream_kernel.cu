@@ -282,7 +282,192 @@ __global__ void __launch_bounds__(32) dtw_pairs_stream_kernel(DtwPairsArgs a, in
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Two-rows-per-step variant: a step handles template rows (2u-1, 2u) of the lane's block, i.e. a
+// 2 x 8 tile of cells = 128 FFMA2 for 8 LDS.128 + 2 shuffles + 2 band masks. Five lanes per pair
+// (a block's 2*window+7 rows take <= 25 steps, the lane period is 5*L = 25 steps: window <= 21),
+// six pairs per warp.
+constexpr int L2 = 5;
+constexpr int PPW2 = 6;
+constexpr int LAS = 3;     // prefetch distance in steps (two rows each)
+constexpr int PAIR_FLOATS2 = RING * RS + 4;  // +4 floats: best bank phase found for 5 lanes reading rows two apart
+
+__global__ void __launch_bounds__(32) dtw_pairs_stream2_kernel(DtwPairsArgs a, int64_t n_groups, int window) {
+    __shared__ __align__(16) float ring_all[PPW2 * PAIR_FLOATS2];
+    const int lane = threadIdx.x;
+    const int g = lane / L2, l = lane - g * L2;
+    const int m = a.tmpl_len_max, n = a.win_len_max;
+    const int w = window;
+    const int n_blocks = (n + CB - 1) / CB;
+    const int last_row = m - 1;
+    const int steps = (last_row + 1) / 2 + (n_blocks - 1);
+    const int left_lane = l == 0 ? lane + (L2 - 1) : lane - 1;
+    float* ring = ring_all + (g < PPW2 ? g : 0) * PAIR_FLOATS2;
+
+    auto costs = [&](int r, const f2 (&bcol)[CB][8], float (&cost)[CB]) {
+        const float* arow = ring + (r & (RING - 1)) * RS;
+        f2 ar[8];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(arow + 4 * q);
+            ar[2 * q] = v.x;
+            ar[2 * q + 1] = v.y;
+        }
+        f2 na2 = mul2(ar[0], ar[0]);
+#pragma unroll
+        for (int q = 1; q < 8; q++) na2 = fma2(ar[q], ar[q], na2);
+        const float na = hsum(na2);
+        const float inva = na > 0.f ? rsqrtf(na) : 0.f;
+#pragma unroll
+        for (int j = 0; j < CB; j++) {
+            f2 acc = mul2(ar[0], bcol[j][0]);
+#pragma unroll
+            for (int q = 1; q < 8; q++) acc = fma2(ar[q], bcol[j][q], acc);
+            cost[j] = fmaf(hsum(acc), inva, 1.f);
+        }
+    };
+    auto issue_rows = [&](const float* tmpl, bool valid, int step) {  // rows 2*step-1 and 2*step
+#pragma unroll
+        for (int k = 1; k >= 0; k--) {
+            const int row = 2 * step - k;
+            if (valid && l < 4 && row <= last_row)
+                cp_async16(ring + (row & (RING - 1)) * RS + 4 * l, tmpl + (size_t)(row - 1) * kD + 4 * l);
+        }
+        cp_async_commit();
+    };
+
+    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const int64_t p = grp * PPW2 + g;
+        const bool valid = g < PPW2 && p < a.n_pairs;
+        const float* tmpl = a.tmpl + (a.tmpl_off && valid ? a.tmpl_off[p] : (valid ? p : 0) * (int64_t)m * kD);
+        const float* win = a.win + (a.win_off && valid ? a.win_off[p] : (valid ? p : 0) * (int64_t)n * kD);
+
+        __syncwarp();
+#pragma unroll
+        for (int st = 1; st <= LAS; st++) issue_rows(tmpl, valid, st);
+
+        int B = l;
+        BlockInfo bi = block_info(B, n, n_blocks, w, last_row, valid);
+        f2 bcol[CB][8];
+        if (valid && B < n_blocks) {
+            load_block(win, n, B, bcol);
+            if (B + L2 < n_blocks) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) prefetch_l2(win + (size_t)(B + L2) * CB * kD + 32 * k);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < CB; j++)
+#pragma unroll
+                for (int q = 0; q < 8; q++) bcol[j][q] = 0ull;
+        }
+        float Dcol[CB];
+#pragma unroll
+        for (int j = 0; j < CB; j++) Dcol[j] = INFINITY;
+        float diag_in = (l == 0) ? 0.f : INFINITY;   // D[0][0]
+        float out1 = INFINITY, out2 = INFINITY;
+        float result = INFINITY;
+
+        for (int st = 1; st <= steps; st++) {
+            cp_async_wait<LAS - 1>();   // rows 2*st-1, 2*st have landed
+            __syncwarp();
+            const float shf1 = __shfl_sync(0xffffffffu, out1, left_lane);
+            const float shf2 = __shfl_sync(0xffffffffu, out2, left_lane);
+            const int u = st - B;
+            const int r1 = 2 * u - 1, r2 = 2 * u;
+            const bool act1 = r1 >= bi.rlo && r1 <= bi.rhi;
+            const bool act2 = r2 >= bi.rlo && r2 <= bi.rhi;
+            const int cl = bi.c0 - 1;   // left neighbour column
+            const bool ok1 = bi.left_possible && r1 >= 1 && cl >= r1 - w && cl <= r1 + w - 1;
+            const bool ok2 = bi.left_possible && r2 >= 1 && cl >= r2 - w && cl <= r2 + w - 1;
+            const float li1 = ok1 ? shf1 : INFINITY;
+            const float li2 = ok2 ? shf2 : INFINITY;
+            const int jlo1 = max(0, r1 - w - bi.c0), jhi1 = min(bi.jmax, r1 + w - 1 - bi.c0);
+            const int jlo2 = max(0, r2 - w - bi.c0), jhi2 = min(bi.jmax, r2 + w - 1 - bi.c0);
+            const unsigned mask1 = act1 ? ((2u << jhi1) - (1u << jlo1)) : 0u;
+            const unsigned mask2 = act2 ? ((2u << jhi2) - (1u << jlo2)) : 0u;
+
+            float c1[CB], c2[CB];
+            costs(max(r1, 1), bcol, c1);
+            costs(max(r2, 1), bcol, c2);
+
+            float D1[CB];
+            {
+                float left = li1, diag = diag_in;
+#pragma unroll
+                for (int j = 0; j < CB; j++) {
+                    const float up = Dcol[j];
+                    float v = c1[j] + min3(up, diag, left);
+                    v = (mask1 >> j) & 1u ? v : INFINITY;
+                    diag = up;
+                    left = v;
+                    D1[j] = v;
+                }
+            }
+            {
+                float left = li2, diag = li1;
+#pragma unroll
+                for (int j = 0; j < CB; j++) {
+                    const float up = D1[j];
+                    float v = c2[j] + min3(up, diag, left);
+                    v = (mask2 >> j) & 1u ? v : INFINITY;
+                    diag = up;
+                    left = v;
+                    Dcol[j] = v;
+                }
+            }
+            out1 = D1[CB - 1];
+            out2 = Dcol[CB - 1];
+            if (r1 == last_row || r2 == last_row) {
+                const int jn = n - bi.c0;
+#pragma unroll
+                for (int j = 0; j < CB; j++)
+                    if (j == jn) result = (r1 == last_row) ? D1[j] : Dcol[j];
+            }
+            diag_in = li2;
+
+            if ((act1 || act2) && r2 >= bi.rhi) {   // block finished: next block of this lane
+                B += L2;
+                bi = block_info(B, n, n_blocks, w, last_row, valid);
+                if (B < n_blocks) {
+                    load_block(win, n, B, bcol);
+                    if (B + L2 < n_blocks) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) prefetch_l2(win + (size_t)(B + L2) * CB * kD + 32 * k);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < CB; j++) Dcol[j] = INFINITY;
+                diag_in = INFINITY;
+                // out1/out2 are kept: the right-hand neighbour reads them on the next step
+            }
+            issue_rows(tmpl, valid, st + LAS);
+            if (st == steps / 2 && grp + gridDim.x < n_groups) {   // warm L2 for the next group
+                const int64_t pn = p + (int64_t)gridDim.x * PPW2;
+                if (g < PPW2 && pn < a.n_pairs && !a.win_off) {
+                    const float* wn = a.win + pn * (int64_t)n * kD + (size_t)l * CB * kD;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) prefetch_l2(wn + 32 * k);
+                    if (l < 4) prefetch_l2(a.tmpl + pn * (int64_t)m * kD + 32 * l);
+                }
+            }
+        }
+        cp_async_wait<0>();
+        float mine = INFINITY;
+#pragma unroll
+        for (int k = 0; k < L2; k++) mine = fminf(mine, __shfl_sync(0xffffffffu, result, min(g * L2 + k, 31)));
+        if (valid && l == 0) {
+            const float cst = m >= 2 ? mine : INFINITY;
+            const float normalized = __fdiv_rn(cst, (float)(m + n));
+            a.out[p] = __fdiv_rn(1.f, 1.f + expf(__fdiv_rn(normalized - a.score_ref, a.score_ref)));
+        }
+    }
+}
+
 }  // namespace
+
+int g_stream_rows = 0;  // 0 = automatic, 1 = force the one-row-per-step kernel (A/B measurements)
+void set_dtw_stream_rows(int rows) { g_stream_rows = rows; }
 
 bool dtw_pairs_stream_supported(const DtwPairsArgs& a) {
     if (a.d != kD || a.cmn || a.tmpl_len || a.win_len) return false;
@@ -302,16 +487,22 @@ cudaError_t launch_dtw_pairs_stream(const DtwPairsArgs& a, cudaStream_t stream) 
     const int diff = m > n ? m - n : n - m;
     const int window = a.band > diff ? a.band : diff;
     const int64_t n_groups = (a.n_pairs + PPW - 1) / PPW;
-    int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dtw_pairs_stream_kernel, 32, 0);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int n_blocks = (n + CB - 1) / CB;
+    // two-rows-per-step variant: window <= 21 and rows in flight (2*(n_blocks-1)+2 behind, 2*LAS ahead) fit the ring
+    const bool two_rows = g_stream_rows != 1 && window <= 21 && 2 * (n_blocks - 1) + 2 + 2 * LAS <= RING;
+    int per_sm = 0;
+    cudaError_t e = two_rows ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dtw_pairs_stream2_kernel, 32, 0)
+                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dtw_pairs_stream_kernel, 32, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    const int64_t groups = two_rows ? (a.n_pairs + PPW2 - 1) / PPW2 : n_groups;
     int64_t blocks = (int64_t)sms * per_sm;
-    if (blocks > n_groups) blocks = n_groups;
-    dtw_pairs_stream_kernel<<<(unsigned)blocks, 32, 0, stream>>>(a, n_groups, window);
+    if (blocks > groups) blocks = groups;
+    if (two_rows) dtw_pairs_stream2_kernel<<<(unsigned)blocks, 32, 0, stream>>>(a, groups, window);
+    else dtw_pairs_stream_kernel<<<(unsigned)blocks, 32, 0, stream>>>(a, groups, window);
     return cudaGetLastError();
 }
 

@@ -51,6 +51,7 @@ cudaError_t launch_dtw_pairs_generic(const DtwPairsArgs& a, cudaStream_t stream)
 // window = max(band, |m-n|) <= 23.
 bool dtw_pairs_stream_supported(const DtwPairsArgs& a);
 cudaError_t launch_dtw_pairs_stream(const DtwPairsArgs& a, cudaStream_t stream);
+void set_dtw_stream_rows(int rows);
 
 // Pipeline scoring: every new frame j of every stream closes a window; slot s scores the first
 // slot_len[s] frames of that window (after CMN) against template s.

@@ -96,7 +96,8 @@ def test_dtw_kernel_matches_oracle(m, n, d, band, cmn):
         ref.append(O.compare(a[p], wb, band, 0.22))
     # variant 1 = generic kernel (reference operation order, held to 5e-6); 0 = automatic choice
     # (streaming kernel where it applies; FFMA2 dots + rsqrt change the rounding, held to 3e-5)
-    for variant, tol in ((1, 5e-6), (0, 3e-5)):
+    # 3 = the one-row-per-step streaming kernel (0 prefers the two-rows-per-step one)
+    for variant, tol in ((1, 5e-6), (0, 3e-5), (3, 3e-5)):
         rp.set_dtw_variant(variant)
         got = rp.dtw_scores(torch.from_numpy(a).cuda(), torch.from_numpy(w).cuda(), band=band, cmn=cmn).cpu().numpy()
         rp.set_dtw_variant(0)
@@ -118,10 +119,12 @@ def test_dtw_stream_kernel_many_pairs_vs_generic():
     w = torch.randn((P, 100, 16), device="cuda", generator=g) * scale
     rp.set_dtw_variant(1)
     ref = rp.dtw_scores(a, w, band=5)
-    rp.set_dtw_variant(0)
-    got = rp.dtw_scores(a, w, band=5)
-    rel = ((got - ref).abs() / ref.abs().clamp_min(1e-12)).max().item()
-    assert rel < 3e-5, rel
+    for variant in (0, 3):
+        rp.set_dtw_variant(variant)
+        got = rp.dtw_scores(a, w, band=5)
+        rp.set_dtw_variant(0)
+        rel = ((got - ref).abs() / ref.abs().clamp_min(1e-12)).max().item()
+        assert rel < 3e-5, (variant, rel)
     assert float(ref.min()) > 0
 
 
