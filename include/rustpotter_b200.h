@@ -189,6 +189,9 @@ int rp_dtw_scores(const float* tmpl_dev, const int64_t* tmpl_off_dev, const int3
 /* Selects the DTW kernel variant for rp_dtw_scores (0 = automatic, 1 = generic wavefront kernel,
  * 2 = tuned streaming kernel where applicable). For A/B measurements. */
 int rp_set_dtw_variant(int variant);
+/* Selects the MFCC kernel: 0 = automatic (two-frames-per-warp TMA-staged kernel where it applies), 1 = one frame
+ * per warp. For A/B measurements and parity tests. */
+int rp_set_mfcc_variant(int variant);
 
 /* =============================================================================================
  * Host-logic hooks (no GPU needed): used by the CPU test-suite to exercise the wakeword-file

@@ -84,7 +84,7 @@ EXPORTED = [
     "rp_batch_add_wakeword_from_buffer", "rp_batch_add_wakeword_from_file", "rp_batch_remove_wakewords",
     "rp_batch_set_cuda_stream", "rp_batch_process", "rp_batch_update_config", "rp_batch_reset",
     "rp_batch_windows_scored", "rp_batch_n_streams", "rp_batch_max_mfcc_frames", "rp_batch_last_timings",
-    "rp_batch_last_launches", "rp_batch_copy_last_scores", "rp_mfcc_frames", "rp_dtw_scores", "rp_set_dtw_variant", "rp_wakeword_inspect",
+    "rp_batch_last_launches", "rp_batch_copy_last_scores", "rp_mfcc_frames", "rp_dtw_scores", "rp_set_dtw_variant", "rp_set_mfcc_variant", "rp_wakeword_inspect",
     "rp_wakeword_template", "rp_host_replay",
 ]
 
@@ -145,6 +145,7 @@ def lib() -> C.CDLL:
     L.rp_mfcc_frames.argtypes = [vp, C.c_int64, C.c_int64, C.c_int, vp, vp]
     L.rp_dtw_scores.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp]
     L.rp_set_dtw_variant.argtypes = [C.c_int]
+    L.rp_set_mfcc_variant.argtypes = [C.c_int]
     L.rp_wakeword_inspect.argtypes = [u8p, C.c_size_t, C.POINTER(WakewordInfo)]
     L.rp_wakeword_template.argtypes = [u8p, C.c_size_t, C.c_int, C.c_char_p, f32p, C.c_size_t]
     L.rp_host_replay.argtypes = [cfgp, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_int, f32p, C.c_int64, C.c_int, f32p,
@@ -382,6 +383,10 @@ def dtw_scores(tmpl, win, band: int = 5, score_ref: float = 0.22, cmn: bool = Fa
 
 def set_dtw_variant(v: int):
     lib().rp_set_dtw_variant(v)
+
+
+def set_mfcc_variant(v: int):
+    lib().rp_set_mfcc_variant(v)
 
 
 # ---------------------------------------------------------------- host-logic hooks (no GPU)

@@ -101,36 +101,16 @@ int process_samples(rp_handle* h, const T* samples, size_t n, float max_value, r
 }
 
 // device-resident MFCC tables for the raw kernel entry point, one per (device, mfcc_size)
-struct TableCache {
-    DeviceBuffer hamming, tw, mel, centres, dct;
-    MfccTablesDev dev;
-};
 std::mutex g_table_mutex;
-std::map<std::pair<int, int>, std::unique_ptr<TableCache>> g_tables;
+std::map<std::pair<int, int>, std::unique_ptr<DeviceMfccTables>> g_tables;
 
 const MfccTablesDev& tables_for(int device, int mfcc_size, cudaStream_t s) {
     std::lock_guard<std::mutex> lock(g_table_mutex);
     auto key = std::make_pair(device, mfcc_size);
     auto it = g_tables.find(key);
     if (it != g_tables.end()) return it->second->dev;
-    MfccTables t = build_mfcc_tables(mfcc_size);
-    auto c = std::make_unique<TableCache>();
-    auto up = [&](DeviceBuffer& b, const void* p, size_t bytes) {
-        b.reserve(bytes, "mfcc tables");
-        cuda_check(cudaMemcpyAsync(b.as<void>(), p, bytes, cudaMemcpyHostToDevice, s), "mfcc tables");
-    };
-    up(c->hamming, t.hamming.data(), t.hamming.size() * 4);
-    up(c->tw, t.tw480.data(), t.tw480.size() * 4);
-    up(c->mel, t.mel_bank.data(), t.mel_bank.size() * 4);
-    up(c->centres, t.centres.data(), t.centres.size() * 4);
-    up(c->dct, t.dct.data(), t.dct.size() * 4);
-    cuda_check(cudaStreamSynchronize(s), "mfcc tables");
-    c->dev.hamming = c->hamming.as<float>();
-    c->dev.tw480 = c->tw.as<float2>();
-    c->dev.mel_bank = c->mel.as<float>();
-    c->dev.centres = c->centres.as<int>();
-    c->dev.dct = c->dct.as<float>();
-    c->dev.num_coefficients = t.num_coefficients;
+    auto c = std::make_unique<DeviceMfccTables>();
+    c->upload(mfcc_size, s);
     auto& ref = *c;
     g_tables[key] = std::move(c);
     return ref.dev;
@@ -443,6 +423,11 @@ int rp_set_dtw_variant(int v) {
     // 0 automatic, 1 generic kernel, 2 tuned kernels, 3 tuned with the one-row-per-step streaming kernel
     g_dtw_variant = v == 3 ? 2 : v;
     set_dtw_stream_rows(v == 3 ? 1 : 0);
+    return RP_OK;
+}
+
+int rp_set_mfcc_variant(int v) {
+    set_mfcc_variant(v);
     return RP_OK;
 }
 

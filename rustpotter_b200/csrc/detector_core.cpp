@@ -1,5 +1,6 @@
 #include "detector_core.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -89,7 +90,10 @@ void DetectorCore::process(const float* audio, int64_t S, bool on_device, const 
     if (ws_.empty()) return;  // detector.rs:348-350: audio is dropped, extractor untouched
     if (S <= 0 || S % kFrameSamples != 0) throw Error(RP_ERR_INVALID, "samples_per_stream must be a positive multiple of 480");
     const bool vad = params_.vad_mode >= 0;
-    engine_->process(audio, S, on_device, vad, hits_, vad ? &vad_ : nullptr);
+    // leading hops of this call that no stream can turn into a scored window (e.g. a freshly reset batch)
+    int64_t skip = S / kHopSamples;
+    for (const StreamState& st : states_) skip = std::min(skip, st.hops_until_scorable(params_));
+    engine_->process(audio, S, on_device, vad, (int)std::max<int64_t>(skip, 0), hits_, vad ? &vad_ : nullptr);
 
     const auto t0 = std::chrono::steady_clock::now();
     const int64_t n_chunks = S / kFrameSamples;

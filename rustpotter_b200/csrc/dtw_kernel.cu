@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(kGenericWarps * 32) dtw_windows_generic_kernel
         const int64_t w = p / a.n_slots;
         const int j = (int)(w % a.n_new);
         const int64_t b = w / a.n_new;
+        if (j < a.first_window) continue;  // warp-uniform
         PairView pv;
         pv.m = a.slot_len[s];
         pv.n = pv.m;  // cut_and_normalize_frame keeps the first m frames of the window (wakeword_comp.rs:22-27)
@@ -161,6 +162,7 @@ __global__ void judge_windows_kernel(JudgeArgs a) {
     const int64_t total = a.n_streams * (int64_t)a.n_new;
     const int stride = 5 + a.max_templates;
     for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (int64_t)gridDim.x * blockDim.x) {
+        if ((int)(w % a.n_new) < a.first_window) continue;
         const float* row = a.scores + w * a.n_slots;
         const Judgement jd = judge_window(row, a.metas, a.n_wakewords, a.score_mode);
         if (jd.wakeword < 0) continue;

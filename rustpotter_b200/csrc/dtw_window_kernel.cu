@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(kThreads) dtw_windows_d16_kernel(DtwWindowsArg
     const int64_t rest = cta / a.n_slots;
     const int jb = (int)(rest % j_blocks);
     const int64_t b = rest / j_blocks;
-    const int j0 = jb * kNW;
+    const int j0 = a.first_window + jb * kNW;
     const int m = a.slot_len[s];
 
     // ---- stage the frame tile and the template in shared memory
@@ -272,7 +272,8 @@ __global__ void __launch_bounds__(kThreads) dtw_windows_d16_kernel(DtwWindowsArg
 cudaError_t launch_dtw_windows_d16(const DtwWindowsArgs& a, const float* tmpl_unit, cudaStream_t stream) {
     if (a.d != kD || a.band != 5) return cudaErrorInvalidValue;
     constexpr int W = 5;
-    const int j_blocks = (a.n_new + kNW - 1) / kNW;
+    const int j_blocks = (a.n_new - a.first_window + kNW - 1) / kNW;
+    if (j_blocks <= 0) return cudaSuccess;
     const int64_t ctas = a.n_streams * (int64_t)j_blocks * a.n_slots;
     if (ctas <= 0) return cudaSuccess;
     if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;

@@ -24,13 +24,34 @@ void DeviceBuffer::reserve(size_t bytes, const char* what) {
     bytes_ = bytes;
 }
 
-namespace {
 template <typename T>
-void upload(DeviceBuffer& buf, const std::vector<T>& v, cudaStream_t s, const char* what) {
+static void upload(DeviceBuffer& buf, const std::vector<T>& v, cudaStream_t s, const char* what) {
     buf.reserve(std::max<size_t>(v.size() * sizeof(T), 16), what);
     if (!v.empty()) cuda_check(cudaMemcpyAsync(buf.as<void>(), v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s), what);
 }
-}  // namespace
+
+void DeviceMfccTables::upload(int mfcc_size, cudaStream_t stream) {
+    MfccTables t = build_mfcc_tables(mfcc_size);
+    rp::upload(hamming, t.hamming, stream, "hamming");
+    rp::upload(tw480, t.tw480, stream, "twiddles");
+    rp::upload(mel_bank, t.mel_bank, stream, "mel bank");
+    rp::upload(centres, t.centres, stream, "mel centres");
+    rp::upload(dct, t.dct, stream, "dct");
+    rp::upload(up_weight, t.up_weight, stream, "mel up weights");
+    rp::upload(chunks, t.chunks, stream, "mel chunks");
+    rp::upload(seg_chunks, t.seg_chunks, stream, "mel segments");
+    cuda_check(cudaStreamSynchronize(stream), "mfcc tables");
+    dev.hamming = hamming.as<float>();
+    dev.tw480 = tw480.as<float2>();
+    dev.mel_bank = mel_bank.as<float>();
+    dev.centres = centres.as<int>();
+    dev.dct = dct.as<float>();
+    dev.num_coefficients = t.num_coefficients;
+    dev.up_weight = up_weight.as<float>();
+    dev.chunks = chunks.as<int4>();
+    dev.seg_chunks = seg_chunks.as<int2>();
+    dev.n_chunks = t.n_chunks;
+}
 
 Engine::Engine(int device, int64_t n_streams) : device_(device), n_streams_(n_streams) {
     int count = 0;
@@ -120,18 +141,7 @@ void Engine::configure(const WakewordSet& ws, const rp_config& cfg) {
     upload(metas_, ws.metas, stream_, "wakeword metas");
 
     if (d_ != old_d) {  // set_out_size (extractor.rs:47-59): new filter bank, extractor reset
-        MfccTables t = build_mfcc_tables(d_);
-        upload(hamming_, t.hamming, stream_, "hamming");
-        upload(tw480_, t.tw480, stream_, "twiddles");
-        upload(mel_bank_, t.mel_bank, stream_, "mel bank");
-        upload(centres_, t.centres, stream_, "mel centres");
-        upload(dct_, t.dct, stream_, "dct");
-        tables_.hamming = hamming_.as<float>();
-        tables_.tw480 = tw480_.as<float2>();
-        tables_.mel_bank = mel_bank_.as<float>();
-        tables_.centres = centres_.as<int>();
-        tables_.dct = dct_.as<float>();
-        tables_.num_coefficients = t.num_coefficients;
+        mfcc_tables_.upload(d_, stream_);
         frames_[0].release();
         frames_[1].release();
         frames_cap_ = 0;
@@ -181,8 +191,8 @@ void Engine::ensure_frames(int n_new) {
     frames_cap_ = n_new;
 }
 
-void Engine::process(const float* audio, int64_t S, bool on_device, bool want_vad, std::vector<HitRecord>& hits,
-                     std::vector<float>* vad) {
+void Engine::process(const float* audio, int64_t S, bool on_device, bool want_vad, int first_window,
+                     std::vector<HitRecord>& hits, std::vector<float>* vad) {
     hits.clear();
     if (n_slots_ == 0) return;
     cuda_check(cudaSetDevice(device_), "cudaSetDevice");
@@ -232,7 +242,7 @@ void Engine::process(const float* audio, int64_t S, bool on_device, bool want_va
         float* fb = fb_all + b0 * rows * d_;
         float* carry = carry_.as<float>() + b0 * 2 * kHopSamples;
         // K1: frame j of this call ends at new hop j and starts two hops earlier (carry or earlier audio)
-        cuda_check(launch_mfcc_frames(src, S, carry, nb, n_new, -2 * kHopSamples, tables_, fb, rows, hist_,
+        cuda_check(launch_mfcc_frames(src, S, carry, nb, n_new, -2 * kHopSamples, mfcc_tables_.dev, fb, rows, hist_,
                                       vad_dev ? vad_dev + b0 * n_new : nullptr, stream_), "mfcc kernel");
         cuda_check(launch_copy_rows(src + (S - 2 * kHopSamples), S, carry, 2 * kHopSamples, nb, 2 * kHopSamples, stream_),
                    "carry update");
@@ -253,6 +263,7 @@ void Engine::process(const float* audio, int64_t S, bool on_device, bool want_va
         wa.band = band_;
         wa.score_ref = score_ref_;
         wa.scores = tscore_.as<float>() + b0 * (int64_t)n_new * n_slots_;
+        wa.first_window = std::min(std::max(first_window, 0), n_new);
         if (d_ == 16 && band_ == 5 && dtw_variant_ != 1)
             cuda_check(launch_dtw_windows_d16(wa, tmpl_unit_.as<float>(), stream_), "dtw window kernel");
         else
@@ -270,6 +281,7 @@ void Engine::process(const float* audio, int64_t S, bool on_device, bool want_va
         ja.hits = hits_.as<float>();
         ja.capacity = n_windows;
         ja.stream_base = (int)b0;
+        ja.first_window = wa.first_window;
         cuda_check(launch_judge_windows(ja, stream_), "judge kernel");
         // next call's history = the last hist_ rows of [history | new frames]
         if (hist_ > 0)

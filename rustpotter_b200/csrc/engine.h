@@ -37,6 +37,13 @@ class DeviceBuffer {
     size_t bytes_ = 0;
 };
 
+// MFCC tables resident on the current device.
+struct DeviceMfccTables {
+    DeviceBuffer hamming, tw480, mel_bank, centres, dct, up_weight, chunks, seg_chunks;
+    MfccTablesDev dev;
+    void upload(int mfcc_size, cudaStream_t stream);
+};
+
 struct HitRecord {     // one judged detection of K3, host copy
     int32_t stream, frame, wakeword;
     float avg_score, score;
@@ -60,7 +67,8 @@ class Engine {
 
     // Scores samples_per_stream/160 new hops per stream. Returns the hits sorted by (stream, frame);
     // `vad` (if want_vad) receives [n_streams][n_hops] mean |mfcc| per new frame.
-    void process(const float* audio, int64_t samples_per_stream, bool on_device, bool want_vad,
+    // first_window: no stream can use the windows that end before this new hop (fresh / just-reset streams).
+    void process(const float* audio, int64_t samples_per_stream, bool on_device, bool want_vad, int first_window,
                  std::vector<HitRecord>& hits, std::vector<float>* vad);
 
     // diagnostics
@@ -89,8 +97,7 @@ class Engine {
     float score_ref_ = 0.22f;
     DeviceBuffer tmpl_, tmpl_unit_, slot_off_, slot_len_, metas_;
     // MFCC tables on device
-    DeviceBuffer hamming_, tw480_, mel_bank_, centres_, dct_;
-    MfccTablesDev tables_;
+    DeviceMfccTables mfcc_tables_;
     // per-stream state
     DeviceBuffer carry_;       // [B][320] last two hops of audio
     DeviceBuffer frames_[2];   // [B][hist_ + frames_cap_][d]

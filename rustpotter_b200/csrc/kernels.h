@@ -17,6 +17,11 @@ struct MfccTablesDev {
     const int* centres = nullptr;     // [C+2]
     const float* dct = nullptr;       // [C][C]
     int num_coefficients = 0;         // C
+    // v2 kernel (segment mel sums)
+    const float* up_weight = nullptr; // [240]
+    const int4* chunks = nullptr;     // [32]
+    const int2* seg_chunks = nullptr; // [C+1]
+    int n_chunks = 0;
 };
 
 // K1. Frame j of stream b is built from the 480 samples starting at logical sample
@@ -27,6 +32,8 @@ struct MfccTablesDev {
 cudaError_t launch_mfcc_frames(const float* audio, int64_t audio_stride, const float* carry, int64_t n_streams,
                                int frames_per_stream, int sample_offset0, const MfccTablesDev& t, float* out,
                                int64_t out_stride_frames, int out_row0, float* vad_out, cudaStream_t stream);
+
+void set_mfcc_variant(int v);  // 0 automatic (v2 where it applies), 1 one-frame-per-warp kernel
 
 // Describes the DTW work of one launch of the generic kernel.
 struct DtwPairsArgs {
@@ -70,6 +77,7 @@ struct DtwWindowsArgs {
     int band = 5;
     float score_ref = 0.22f;
     float* scores = nullptr;           // [n_streams][n_new][n_slots]
+    int first_window = 0;              // windows j < first_window are not scored (no stream can use them)
 };
 cudaError_t launch_dtw_windows_generic(const DtwWindowsArgs& a, cudaStream_t stream);
 // Tuned variant for d == 16, band == 5 (dtw_window_kernel.cu). tmpl_unit: the templates of a.tmpl with every row
@@ -91,6 +99,7 @@ struct JudgeArgs {
     float* hits = nullptr;             // device [capacity][5 + max_templates]
     int64_t capacity = 0;
     int stream_base = 0;               // added to the stream index written into hit records (group offset)
+    int first_window = 0;              // windows j < first_window are skipped
 };
 cudaError_t launch_judge_windows(const JudgeArgs& a, cudaStream_t stream);
 

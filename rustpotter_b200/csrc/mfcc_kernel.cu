@@ -21,6 +21,7 @@
 // butterflies may contract (the reference's FFT is a third-party crate whose rounding order is
 // not part of its contract). No fast-math: denormal mel energies must not flush to zero.
 #include <cfloat>
+#include <cstdint>
 
 #include "kernels.h"
 
@@ -190,6 +191,274 @@ mfcc_frames_kernel(const float* __restrict__ audio, int64_t audio_stride, const 
     }
 }
 
+// =============================================================================================
+// K1 v2 — two frames per warp, TMA-staged samples.
+//   * A CTA (8 warps) produces 16 consecutive frames of one stream. Their 18 hops of samples are
+//     contiguous in HBM and are staged into shared memory by ONE bulk asynchronous copy
+//     (cp.async.bulk -> UBLKCP, completion on an mbarrier); the first CTA of a streaming call adds a second
+//     bulk copy for the two carried hops.
+//   * Warp w packs frame A = 2w (real part) and frame B = 2w+1 (imaginary part) into one complex
+//     480-point FFT (same 15 x 32 factorisation as v1) and separates the two spectra afterwards:
+//     X_A[k] = (Z[k] + conj Z[480-k]) / 2,  X_B[k] = (Z[k] - conj Z[480-k]) / 2i; Z[480-k] lives in lane
+//     31-k2 (index 15-k1), one shuffle pair per bin.
+//   * Mel energies from per-segment sums (see mfcc_tables.h): each lane sums one chunk of bins, S = sum p
+//     and U = sum p*up_weight; filter i = U_i + (S_{i+1} - U_{i+1}).
+//   * DCT: lanes 0..15 produce c1..c16 of frame A, lanes 16..31 those of frame B (reference summation
+//     order, un-fused), so the two frames leave as one coalesced 128-byte store.
+// Requires mfcc_size <= 16 and 16-byte aligned stream rows; otherwise v1 is used.
+constexpr int kFramesPerCta = 16;
+constexpr int kTileHops = kFramesPerCta + 2;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
+mfcc_frames2_kernel(const float* __restrict__ audio, int64_t audio_stride, const float* __restrict__ carry,
+                    int frames_per_stream, int sample_offset0, MfccTablesDev t, float* __restrict__ out,
+                    int64_t out_stride_frames, int out_row0, float* __restrict__ vad_out, int ctas_per_stream) {
+    __shared__ __align__(16) float xs[kTileHops * kHop];
+    __shared__ float pw[kWarpsPerBlock][2][kBins];
+    __shared__ float part_s[kWarpsPerBlock][2][32], part_u[kWarpsPerBlock][2][32];
+    __shared__ float lbuf[kWarpsPerBlock][2][32];
+    __shared__ __align__(8) unsigned long long bar;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t b = blockIdx.x / ctas_per_stream;
+    const int j0 = (int)(blockIdx.x - b * ctas_per_stream) * kFramesPerCta;
+    const int nf = min(kFramesPerCta, frames_per_stream - j0);          // frames of this CTA
+    const int64_t g0 = (int64_t)kHop * j0 + sample_offset0;             // logical sample of xs[0]
+    const int n_samples = (nf + 2) * kHop;
+
+    // ---- stage the samples: bulk async copy, completion counted in bytes on the mbarrier
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned bar_a = smem_u32(&bar);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(n_samples * 4) : "memory");
+        int from_carry = 0;
+        if (g0 < 0) {  // the two hops kept from the previous call
+            from_carry = (int)(-g0);
+            const float* src = carry + b * (2 * kHop) + (2 * kHop - from_carry);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(xs)), "l"(src), "r"(from_carry * 4), "r"(bar_a) : "memory");
+        }
+        const float* src = audio + b * audio_stride + (g0 < 0 ? 0 : g0);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(xs + from_carry)), "l"(src), "r"((n_samples - from_carry) * 4), "r"(bar_a) : "memory");
+    }
+    {   // every thread waits for phase 0 of the barrier
+        const unsigned bar_a = smem_u32(&bar);
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_LOOP:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+            "@p bra WAIT_DONE;\n"
+            "bra WAIT_LOOP;\n"
+            "WAIT_DONE:\n"
+            "}\n" ::"r"(bar_a) : "memory");
+    }
+
+    const int fa = 2 * warp;            // frame A of this warp inside the CTA (frame B = fa + 1)
+    if (fa >= nf) return;
+    const bool has_b = fa + 1 < nf;
+    const int n2 = (int)(__brev((unsigned)lane) >> 27);
+    const int C = t.num_coefficients, D = C - 1;
+    const float* xa = xs + fa * kHop;
+
+    // Frames A and B are packed as real / imaginary part of one complex FFT. Dynamic-range guard: packing
+    // lets the weaker frame inherit the rounding noise of the stronger one (relative error ~ eps * amplitude
+    // ratio; an exactly silent frame would come out as the other frame's noise floor instead of the zeros
+    // the reference computes). If the two frame energies differ by more than 256x, frame A is transformed
+    // alone and a second pass (rare, warp-uniform) reloads frame B from shared memory.
+    float* pwa = pw[warp][0];
+    float* pwb = pw[warp][1];
+    bool split = false;
+    int pass = 0;
+    do {
+        // ---- load, pre-emphasis (restarts at every hop), Hamming; the two frames are 160 samples apart
+        const float* xp = pass == 0 ? xa : xa + kHop;   // frame that goes to the real slot
+        float xr[15], xi[15];
+#pragma unroll
+        for (int i = 0; i < 15; i++) {
+            const int s = 32 * i + n2;
+            const float h = __ldg(t.hamming + s);
+            const bool second = pass == 0 && has_b;      // imaginary slot <- frame B
+            const float x0 = xp[s], x1 = second ? xp[s + kHop] : 0.f;
+            float y0 = x0, y1 = x1;
+            if (s % kHop != 0) {
+                y0 = __fsub_rn(x0, __fmul_rn(kPre, xp[s - 1]));
+                y1 = second ? __fsub_rn(x1, __fmul_rn(kPre, xp[s + kHop - 1])) : 0.f;
+            }
+            xr[i] = __fmul_rn(y0, h);
+            xi[i] = __fmul_rn(y1, h);
+        }
+        if (pass == 0 && has_b) {
+            float ea = 0.f, eb = 0.f;
+#pragma unroll
+            for (int i = 0; i < 15; i++) {
+                ea = fmaf(xr[i], xr[i], ea);
+                eb = fmaf(xi[i], xi[i], eb);
+            }
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+                ea += __shfl_xor_sync(0xffffffffu, ea, o);
+                eb += __shfl_xor_sync(0xffffffffu, eb, o);
+            }
+            split = !(ea <= 256.f * eb && eb <= 256.f * ea);
+            if (split) {
+#pragma unroll
+                for (int i = 0; i < 15; i++) xi[i] = 0.f;
+            }
+        }
+        // ---- per-lane 15-point DFTs of the two real sequences, merged into Z = Y_r + i Y_i
+        float re[15], im[15];
+        {
+            float sa[8], da[8], sb[8], db[8];
+#pragma unroll
+            for (int i = 1; i <= 7; i++) {
+                sa[i] = xr[i] + xr[15 - i];
+                da[i] = xr[i] - xr[15 - i];
+                sb[i] = xi[i] + xi[15 - i];
+                db[i] = xi[i] - xi[15 - i];
+            }
+            float ra0 = xr[0], rb0 = xi[0];
+#pragma unroll
+            for (int i = 1; i <= 7; i++) {
+                ra0 += sa[i];
+                rb0 += sb[i];
+            }
+            re[0] = ra0;
+            im[0] = rb0;
+#pragma unroll
+            for (int k = 1; k <= 7; k++) {
+                float ra = xr[0], qa = 0.f, rb = xi[0], qb = 0.f;
+#pragma unroll
+                for (int i = 1; i <= 7; i++) {
+                    const float c = cos15((i * k) % 15), sn = sin15((i * k) % 15);
+                    ra = fmaf(sa[i], c, ra);
+                    qa = fmaf(da[i], sn, qa);
+                    rb = fmaf(sb[i], c, rb);
+                    qb = fmaf(db[i], sn, qb);
+                }
+                // Y_r[k] = ra - i qa, Y_r[15-k] = ra + i qa (same for the imaginary-slot frame);  Z = Y_r + i Y_i
+                re[k] = ra + qb;
+                im[k] = rb - qa;
+                re[15 - k] = ra - qb;
+                im[15 - k] = rb + qa;
+            }
+        }
+        // ---- twiddle W480^(n2*k1)
+#pragma unroll
+        for (int k = 1; k < 15; k++) {
+            const float2 w = __ldg(t.tw480 + n2 * k);
+            const float r = re[k] * w.x - im[k] * w.y;
+            const float q = re[k] * w.y + im[k] * w.x;
+            re[k] = r;
+            im[k] = q;
+        }
+        // ---- 32-point DIT FFT across lanes (lane k2 ends with Z[k1 + 15*k2])
+        {
+            const bool bottom = lane & 1;
+#pragma unroll
+            for (int k = 0; k < 15; k++) {
+                const float orr = __shfl_xor_sync(0xffffffffu, re[k], 1);
+                const float oi = __shfl_xor_sync(0xffffffffu, im[k], 1);
+                re[k] = bottom ? orr - re[k] : re[k] + orr;
+                im[k] = bottom ? oi - im[k] : im[k] + oi;
+            }
+        }
+#pragma unroll
+        for (int h = 2; h <= 16; h <<= 1) {
+            const bool bottom = (lane & h) != 0;
+            float2 w = __ldg(t.tw480 + (lane & (h - 1)) * (kBins / h));
+            if (bottom) { w.x = -w.x; w.y = -w.y; }
+#pragma unroll
+            for (int k = 0; k < 15; k++) {
+                const float orr = __shfl_xor_sync(0xffffffffu, re[k], h);
+                const float oi = __shfl_xor_sync(0xffffffffu, im[k], h);
+                const float ar = bottom ? orr : re[k], ai = bottom ? oi : im[k];
+                const float br = bottom ? re[k] : orr, bi = bottom ? im[k] : oi;
+                re[k] = ar + (br * w.x - bi * w.y);
+                im[k] = ai + (br * w.y + bi * w.x);
+            }
+        }
+        // ---- separate the two spectra and take |X|^2 for bins < 240 (lanes 0..15)
+        float* dst_r = pass == 0 ? pwa : pwb;   // where the real-slot frame's power goes
+#pragma unroll
+        for (int k = 0; k < 15; k++) {
+            const int kk = k == 0 ? 0 : 15 - k;                        // index of Z[480 - bin] in the partner lane
+            const int partner = k == 0 ? ((32 - lane) & 31) : 31 - lane;
+            const float cr = __shfl_sync(0xffffffffu, re[kk], partner);
+            const float ci = __shfl_sync(0xffffffffu, im[kk], partner);
+            if (lane < 16) {
+                const float ar = re[k] + cr, ai = im[k] - ci;
+                dst_r[k + 15 * lane] = 0.25f * (ar * ar + ai * ai);
+                if (!split) {
+                    const float br = re[k] - cr, bi = im[k] + ci;
+                    pwb[k + 15 * lane] = 0.25f * (br * br + bi * bi);
+                }
+            }
+        }
+        pass++;
+    } while (pass == 1 && split);
+    __syncwarp();
+
+    // ---- mel energies: chunk sums -> segment sums -> filters; ln
+    const int4 ch = lane < t.n_chunks ? __ldg(t.chunks + lane) : make_int4(0, 0, 0, 0);
+#pragma unroll
+    for (int f = 0; f < 2; f++) {
+        const float* p = pw[warp][f];
+        float s = 0.f, u = 0.f;
+        for (int k = ch.y; k < ch.z; k++) {
+            const float e = p[k];
+            s += e;
+            u = fmaf(e, __ldg(t.up_weight + k), u);
+        }
+        part_s[warp][f][lane] = s;
+        part_u[warp][f][lane] = u;
+    }
+    __syncwarp();
+    const int2 sc = lane <= C ? __ldg(t.seg_chunks + lane) : make_int2(0, 0);
+#pragma unroll
+    for (int f = 0; f < 2; f++) {
+        float s = 0.f, u = 0.f;
+        for (int q = 0; q < sc.y; q++) {
+            s += part_s[warp][f][sc.x + q];
+            u += part_u[warp][f][sc.x + q];
+        }
+        const float s_next = __shfl_down_sync(0xffffffffu, s, 1);
+        const float u_next = __shfl_down_sync(0xffffffffu, u, 1);
+        const float mel = u + (s_next - u_next);
+        if (lane < C) lbuf[warp][f][lane] = logf(__fadd_rn(mel, FLT_MIN));
+    }
+    __syncwarp();
+
+    // ---- DCT-II x2, c0 dropped: half-warp per frame, lane (p & 15) -> coefficient k = (p & 15) + 1
+    const int f = lane >> 4, kc = (lane & 15) + 1;
+    float coef = 0.f;
+    if (kc <= D) {
+        const float* drow = t.dct + (size_t)kc * C;
+        const float* lb = lbuf[warp][f];
+        float acc = 0.f;
+        for (int n = 0; n < C; n++) acc = __fadd_rn(acc, __fmul_rn(lb[n], __ldg(drow + n)));
+        coef = __fmul_rn(2.f, acc);
+        if (f == 0 || has_b)
+            out[((b * out_stride_frames) + out_row0 + j0 + fa + f) * (int64_t)D + (kc - 1)] = coef;
+    }
+    if (vad_out != nullptr) {  // mean |mfcc| in coefficient order (vad.rs:12)
+        float s0 = 0.f, s1 = 0.f;
+        for (int k = 0; k < D; k++) {
+            s0 = __fadd_rn(s0, fabsf(__shfl_sync(0xffffffffu, coef, k)));
+            s1 = __fadd_rn(s1, fabsf(__shfl_sync(0xffffffffu, coef, 16 + k)));
+        }
+        if (lane == 0) vad_out[b * frames_per_stream + j0 + fa] = __fdiv_rn(s0, (float)D);
+        if (lane == 16 && has_b) vad_out[b * frames_per_stream + j0 + fa + 1] = __fdiv_rn(s1, (float)D);
+    }
+}
+
 __global__ void copy_rows_kernel(const float* __restrict__ src, int64_t src_stride, float* __restrict__ dst,
                                  int64_t dst_stride, int64_t n_streams, int64_t row_floats) {
     const int64_t total = n_streams * row_floats;
@@ -201,11 +470,26 @@ __global__ void copy_rows_kernel(const float* __restrict__ src, int64_t src_stri
 
 }  // namespace
 
+int g_mfcc_variant = 0;  // 0 automatic, 1 force the one-frame-per-warp kernel
+void set_mfcc_variant(int v) { g_mfcc_variant = v; }
+
 cudaError_t launch_mfcc_frames(const float* audio, int64_t audio_stride, const float* carry, int64_t n_streams,
                                int frames_per_stream, int sample_offset0, const MfccTablesDev& t, float* out,
                                int64_t out_stride_frames, int out_row0, float* vad_out, cudaStream_t stream) {
     const int64_t total = n_streams * (int64_t)frames_per_stream;
     if (total <= 0) return cudaSuccess;
+    const bool aligned = (audio_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(audio) & 15) == 0) &&
+                         (carry == nullptr || (reinterpret_cast<uintptr_t>(carry) & 15) == 0);
+    if (g_mfcc_variant != 1 && t.num_coefficients - 1 <= 16 && t.n_chunks > 0 && aligned && sample_offset0 % 4 == 0) {
+        const int ctas_per_stream = (frames_per_stream + kFramesPerCta - 1) / kFramesPerCta;
+        const int64_t ctas = n_streams * (int64_t)ctas_per_stream;
+        if (ctas <= 0x7fffffffLL) {
+            mfcc_frames2_kernel<<<(unsigned)ctas, kWarpsPerBlock * 32, 0, stream>>>(
+                audio, audio_stride, carry, frames_per_stream, sample_offset0, t, out, out_stride_frames, out_row0, vad_out,
+                ctas_per_stream);
+            return cudaGetLastError();
+        }
+    }
     const int64_t blocks = (total + kWarpsPerBlock - 1) / kWarpsPerBlock;
     mfcc_frames_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(
         audio, audio_stride, carry, total, frames_per_stream, sample_offset0, t, out, out_stride_frames, out_row0, vad_out);

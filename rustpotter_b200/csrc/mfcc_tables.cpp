@@ -1,5 +1,6 @@
 #include "mfcc_tables.h"
 
+#include <algorithm>
 #include <cmath>
 
 #include "rp_internal.h"
@@ -49,6 +50,38 @@ MfccTables build_mfcc_tables(int mfcc_size) {
     const float pi_over_n = kPiF / (float)C;
     for (int k = 0; k < C; k++)
         for (int n = 0; n < C; n++) t.dct[(size_t)k * C + n] = std::cos(pi_over_n * ((float)n + 0.5f) * (float)k);
+    // ---- segment form of the mel bank for the v2 kernel
+    t.up_weight.assign(kSpectrumBins, 0.f);
+    const int n_seg = C + 1;
+    std::vector<int> seg_lo(n_seg), seg_hi(n_seg);
+    for (int j = 0; j < n_seg; j++) {
+        seg_lo[j] = std::min(t.centres[j], kSpectrumBins);
+        seg_hi[j] = std::min(t.centres[j + 1], kSpectrumBins);
+        for (int k = seg_lo[j]; k < seg_hi[j]; k++) t.up_weight[k] = (float)(k - t.centres[j]) / (float)(t.centres[j + 1] - t.centres[j]);
+    }
+    t.chunks.assign(32 * 4, 0);
+    t.seg_chunks.assign((size_t)n_seg * 2, 0);
+    t.n_chunks = 0;
+    if (n_seg > 32) return t;  // one chunk per lane at least: the two-frames-per-warp kernel needs mfcc_size <= 16 anyway
+    int max_len = 1;
+    for (;; max_len++) {  // smallest chunk length that fits all segments into 32 chunks
+        int total = 0;
+        for (int j = 0; j < n_seg; j++) total += std::max(1, (seg_hi[j] - seg_lo[j] + max_len - 1) / max_len);
+        if (total <= 32) break;
+    }
+    int c = 0;
+    for (int j = 0; j < n_seg; j++) {
+        const int len = seg_hi[j] - seg_lo[j];
+        const int parts = std::max(1, (len + max_len - 1) / max_len);
+        t.seg_chunks[2 * j] = c;
+        t.seg_chunks[2 * j + 1] = parts;
+        for (int q = 0; q < parts; q++, c++) {
+            t.chunks[4 * c] = j;
+            t.chunks[4 * c + 1] = seg_lo[j] + (int)((long long)len * q / parts);
+            t.chunks[4 * c + 2] = seg_lo[j] + (int)((long long)len * (q + 1) / parts);
+        }
+    }
+    t.n_chunks = c;
     return t;
 }
 

@@ -89,6 +89,12 @@ class StreamState {
     // and VAD is off (nothing can fire); O(1).
     void skip_hops(const DetectorParams& p, int64_t n);
     bool idle() const { return !partial_.has_value(); }
+    // Number of coming hops that cannot close a scorable window (extractor warm-up + window fill).
+    int64_t hops_until_scorable(const DetectorParams& p) const {
+        const int64_t warm = kHopsPerChunk - hops_in_ring_;
+        const int64_t fill = p.max_frames - 1 - win_len_;
+        return warm + (fill > 0 ? fill : 0);
+    }
     const std::optional<PartialDetection>& partial() const { return partial_; }
     uint64_t windows_scored() const { return windows_scored_; }
     void clamp_window(int max_frames);          // after a wakeword change (see DESIGN.md deviations)

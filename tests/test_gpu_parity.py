@@ -24,19 +24,28 @@ def _torch():
 
 
 # ------------------------------------------------------------------ K1
-@pytest.mark.parametrize("d", [5, 16, 13, 31])
-def test_mfcc_kernel_matches_oracle(d):
+@pytest.fixture(params=[0, 1], ids=["mfcc_auto", "mfcc_v1"])
+def mfcc_variant(request):
+    """0 = automatic (two-frames-per-warp TMA kernel for mfcc_size <= 16), 1 = one frame per warp."""
+    rp.set_mfcc_variant(request.param)
+    yield request.param
+    rp.set_mfcc_variant(0)
+
+
+@pytest.mark.parametrize("d", [5, 16, 13, 31, 1])
+@pytest.mark.parametrize("hops", [131, 20, 4, 36])
+def test_mfcc_kernel_matches_oracle(d, hops, mfcc_variant):
     torch = _torch()
-    audio = synth_audio(5, 160 * 131, seed=11)
+    audio = synth_audio(5, 160 * hops, seed=11 + hops)
     got = rp.mfcc_frames(torch.from_numpy(audio).cuda(), d).cpu().numpy()
-    assert got.shape == (5, 128, d)
+    assert got.shape == (5, hops - 3, d)
     for b in range(5):
         want = O.mfcc_stream(audio[b], d)
         err = np.abs(got[b] - want)
         assert err.max() < 1e-3, (d, b, err.max(), np.unravel_index(err.argmax(), err.shape))
 
 
-def test_mfcc_kernel_reproduces_reference_templates():
+def test_mfcc_kernel_reproduces_reference_templates(mfcc_variant):
     """wav -> kernel MFCC -> CMN equals the matrices stored in the reference's .rpw (its own output)."""
     torch = _torch()
     ww = dict(O.Wakeword(open(golden("oye_casa_g.rpw"), "rb").read()).templates)
@@ -49,7 +58,7 @@ def test_mfcc_kernel_reproduces_reference_templates():
         assert m.shape == t.shape and np.abs(m - t).max() < 2e-4, (i, np.abs(m - t).max())
 
 
-def test_mfcc_edge_cases():
+def test_mfcc_edge_cases(mfcc_variant):
     torch = _torch()
     # too short for any frame: 3 hops -> 0 frames (extractor.rs:69-79)
     out = rp.mfcc_frames(torch.zeros((2, 480), device="cuda"), 16)
@@ -63,6 +72,22 @@ def test_mfcc_edge_cases():
     x = np.sign(np.sin(np.arange(160 * 40) * 0.05)).astype(np.float32)
     got = rp.mfcc_frames(torch.from_numpy(x[None]).cuda(), 16).cpu().numpy()[0]
     assert np.abs(got - O.mfcc_stream(x, 16)).max() < 2e-3
+
+
+def test_mfcc_dynamic_range_between_adjacent_frames(mfcc_variant):
+    """Digital silence next to loud audio, and 60 dB level steps: the two-frames-per-warp kernel must not
+    let one frame's rounding noise leak into its neighbour (it splits such pairs)."""
+    torch = _torch()
+    x = synth_audio(3, 160 * 64, seed=123)
+    x[0, 160 * 20:160 * 31] = 0.0                       # hard digital silence inside a stream
+    x[1, : 160 * 17] *= np.float32(1e-3)                 # -60 dB first part
+    x[2, 160 * 9: 160 * 10] = 0.0                       # a single silent hop
+    x[2, 160 * 40:] *= np.float32(3e-4)
+    got = rp.mfcc_frames(torch.from_numpy(x).cuda(), 16).cpu().numpy()
+    for b in range(3):
+        want = O.mfcc_stream(x[b], 16)
+        err = np.abs(got[b] - want)
+        assert err.max() < 1e-3, (b, err.max(), np.unravel_index(err.argmax(), err.shape))
 
 
 # ------------------------------------------------------------------ K2
@@ -325,7 +350,7 @@ def test_batch_vad_on_golden_stream():
         assert bt.windows_scored() == total
 
 
-def test_batch_streaming_equals_bulk():
+def test_batch_streaming_equals_bulk(mfcc_variant):
     """Feeding the same audio in one call, in 7-chunk calls, and chunk by chunk gives the same
     detections (state carried in HBM between calls)."""
     rpw, audio, _ = _batch_case(B=6, n_chunks=140)

@@ -174,3 +174,31 @@ def test_judgement_modes_match_oracle_aggregate():
             d = got[0][1]
             assert d["score"] == O.aggregate(s, mode), (mode, T, d["score"], O.aggregate(s, mode))
             assert d["counter"] == 1 and d["avg_score"] == 0 and list(d["scores"].values()) == list(s)
+
+
+def test_mfcc_tables_build_for_every_mfcc_size(tmp_path):
+    """Host table construction (mel centres, segment chunks of the two-frames-per-warp kernel) terminates
+    and covers all 240 bins for every mfcc_size the path accepts (1..31)."""
+    import subprocess
+    import textwrap
+    src = tmp_path / "t.cpp"
+    src.write_text(textwrap.dedent('''
+        #include "rustpotter_b200/csrc/mfcc_tables.h"
+        #include <cstdio>
+        int main() {
+            for (int d = 1; d <= 31; d++) {
+                auto t = rp::build_mfcc_tables(d);
+                int bins = 0;
+                for (int c = 0; c < t.n_chunks; c++) bins += t.chunks[4 * c + 2] - t.chunks[4 * c + 1];
+                if (t.n_chunks > 32 || (t.n_chunks > 0 && bins != 240) || (d <= 16 && t.n_chunks == 0)) { printf("bad %d\\n", d); return 1; }
+                if ((int)t.centres.size() != d + 3 || t.centres.front() != 0 || t.centres.back() != 240) { printf("centres %d\\n", d); return 1; }
+            }
+            printf("ok\\n");
+            return 0;
+        }
+    '''))
+    exe = tmp_path / "t"
+    subprocess.run(["g++", "-std=c++17", "-I", ROOT, "-o", str(exe), str(src), os.path.join(ROOT, "rustpotter_b200/csrc/mfcc_tables.cpp")],
+                   check=True, timeout=120)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout
