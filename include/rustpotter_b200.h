@@ -186,8 +186,9 @@ int rp_mfcc_frames(const float* audio_dev, int64_t n_streams, int64_t samples_pe
 int rp_dtw_scores(const float* tmpl_dev, const int64_t* tmpl_off_dev, const int32_t* tmpl_len_dev, int tmpl_len_uniform,
                   const float* win_dev, const int64_t* win_off_dev, const int32_t* win_len_dev, int win_len_uniform,
                   int64_t n_pairs, int d, int band, float score_ref, int cmn, float* out_dev, void* cuda_stream);
-/* Selects the DTW kernel variant for rp_dtw_scores (0 = automatic, 1 = generic wavefront kernel,
- * 2 = tuned streaming kernel where applicable). For A/B measurements. */
+/* Selects the DTW kernel variants (0 = automatic, 1 = generic reference-order kernels, 2 = tuned kernels,
+ * 3 = tuned with the one-row-per-step streaming kernel, 4 = tuned with the two-windows-per-thread pipeline
+ * kernel). For A/B measurements and parity tests. */
 int rp_set_dtw_variant(int variant);
 /* Selects the MFCC kernel: 0 = automatic (two-frames-per-warp TMA-staged kernel where it applies), 1 = one frame
  * per warp. For A/B measurements and parity tests. */

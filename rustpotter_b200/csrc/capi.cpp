@@ -281,10 +281,9 @@ int rp_batch_create(const rp_config* cfg, int64_t n_streams, int device, rp_batc
     if (!cfg || !out) return RP_ERR_INVALID;
     *out = nullptr;
     return guarded((rp_batch*)nullptr, [&] {
-        if (cfg->gain_normalizer_enabled || cfg->band_pass_enabled)
-            throw Error(RP_ERR_UNSUPPORTED, "audio filters are not available on the batched front-end yet");
         auto b = std::make_unique<rp_batch>();
         b->core = std::make_unique<DetectorCore>(*cfg, n_streams, device);
+        b->core->enable_device_filters(*cfg);  // gain normaliser / band pass run as a GPU pre-stage
         b->core->engine().set_dtw_variant(g_dtw_variant);
         *out = b.release();
         return RP_OK;
@@ -338,7 +337,8 @@ int rp_batch_process(rp_batch* b, const float* audio, int64_t S, int on_device, 
 int rp_batch_update_config(rp_batch* b, const rp_config* cfg) {
     if (!b || !cfg) return RP_ERR_INVALID;
     return guarded(b, [&] {
-        b->core->update_detector_config(*cfg);
+        b->core->update_detector_config(*cfg);   // update_config = detector config, then filters config (detector.rs:259-262)
+        b->core->update_filters_config(*cfg);
         return RP_OK;
     });
 }
@@ -420,9 +420,11 @@ int rp_dtw_scores(const float* tmpl_dev, const int64_t* tmpl_off_dev, const int3
 }
 
 int rp_set_dtw_variant(int v) {
-    // 0 automatic, 1 generic kernel, 2 tuned kernels, 3 tuned with the one-row-per-step streaming kernel
-    g_dtw_variant = v == 3 ? 2 : v;
+    // 0 automatic, 1 generic kernels, 2 tuned kernels, 3 tuned with the one-row-per-step streaming kernel,
+    // 4 tuned with the two-windows-per-thread pipeline kernel (alternatives kept for A/B measurements)
+    g_dtw_variant = v >= 3 ? 2 : v;
     set_dtw_stream_rows(v == 3 ? 1 : 0);
+    set_dtw_window_kernel(v == 4 ? 2 : 0);
     return RP_OK;
 }
 

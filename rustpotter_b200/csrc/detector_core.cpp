@@ -55,6 +55,7 @@ void DetectorCore::on_wakeword_change() {
     // Deviation: the reference would keep scoring a window longer than the new
     // max_mfcc_frames after a removal; here the window is clamped to the new length.
     for (auto& s : states_) s.clamp_window(params_.max_frames);
+    if (device_filters_) engine_->set_gain_reference(ws_.target_rms_level, ws_.max_frames / 3);  // detector.rs:336-338
 }
 
 void DetectorCore::update_detector_config(const rp_config& cfg) {
@@ -72,6 +73,18 @@ void DetectorCore::update_detector_config(const rp_config& cfg) {
     for (auto& s : states_) s.configure(params_);
     ws_.rebuild(cfg_);
     engine_->configure(ws_, cfg_);
+    reset();
+}
+
+void DetectorCore::enable_device_filters(const rp_config& cfg) {
+    device_filters_ = true;
+    cfg_.gain_normalizer_enabled = cfg.gain_normalizer_enabled;
+    cfg_.band_pass_enabled = cfg.band_pass_enabled;
+    engine_->set_filters(cfg);
+}
+
+void DetectorCore::update_filters_config(const rp_config& cfg) {
+    if (device_filters_) enable_device_filters(cfg);  // fresh filters; gain reference waits for the next wakeword change
     reset();
 }
 
@@ -99,6 +112,7 @@ void DetectorCore::process(const float* audio, int64_t S, bool on_device, const 
     const int64_t n_chunks = S / kFrameSamples;
     const int64_t n_hops = n_chunks * kHopsPerChunk;
     const int64_t B = engine_->n_streams();
+    const float* dev_gains = (device_filters_ && engine_->gain_filter_enabled()) ? engine_->last_gains().data() : nullptr;
     size_t hi = 0;
     for (int64_t b = 0; b < B; b++) {
         StreamState& st = states_[(size_t)b];
@@ -119,7 +133,7 @@ void DetectorCore::process(const float* audio, int64_t S, bool on_device, const 
                     continue;
                 }
             }
-            const float gain = gains ? gains[c] : 1.f;
+            const float gain = gains ? gains[c] : (dev_gains ? dev_gains[(size_t)(b * n_chunks + c)] : 1.f);
             for (int k = 0; k < kHopsPerChunk; k++) {
                 const int64_t j = c * kHopsPerChunk + k;
                 while (hp < hi && hits_[hp].frame < j) hp++;

@@ -26,6 +26,8 @@ class DetectorCore {
     bool remove_wakeword(const std::string& key);  // :180-189
     bool remove_wakewords();                       // :193-202
     void update_detector_config(const rp_config& cfg);  // :265-282
+    void update_filters_config(const rp_config& cfg);   // :283-289 (batched front-end: filters run on the GPU)
+    void enable_device_filters(const rp_config& cfg);   // batched front-end only
     void reset();                                       // :290-302
 
     // n_chunks * 480 samples per stream; gains: per-chunk gain stamped on detections (nullptr = 1.0)
@@ -52,6 +54,7 @@ class DetectorCore {
     std::vector<std::vector<const char*>> names_;  // per wakeword: template names (for rp_detection)
     std::vector<HitRecord> hits_;
     std::vector<float> vad_;
+    bool device_filters_ = false;
 };
 
 }  // namespace rp

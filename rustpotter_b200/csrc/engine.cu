@@ -175,6 +175,47 @@ void Engine::configure(const WakewordSet& ws, const rp_config& cfg) {
     cuda_check(cudaStreamSynchronize(stream_), "configure");
 }
 
+void Engine::set_filters(const rp_config& cfg) {
+    cuda_check(cudaSetDevice(device_), "cudaSetDevice");
+    cuda_check(cudaStreamSynchronize(stream_), "sync");
+    filt_gain_ = cfg.gain_normalizer_enabled != 0;
+    filt_bp_ = cfg.band_pass_enabled != 0;
+    filt_fixed_ref_ = cfg.gain_ref_set != 0;
+    filt_min_gain_ = cfg.min_gain;
+    filt_max_gain_ = cfg.max_gain;
+    filt_ref_ = filt_fixed_ref_ ? cfg.gain_ref : std::nanf("");
+    filt_ref_sqrt_ = filt_fixed_ref_ ? std::sqrt(cfg.gain_ref) : std::nanf("");
+    filt_window_ = 1;  // GainNormalizerFilter::new: window_size 1 until set_rms_level_ref
+    if (filt_gain_) {
+        gain_window_.reserve((size_t)n_streams_ * kGainWindowCap * sizeof(float), "gain window");
+        gain_count_.reserve((size_t)n_streams_ * 2 * sizeof(int), "gain window count");
+        cuda_check(cudaMemsetAsync(gain_count_.as<void>(), 0, (size_t)n_streams_ * 2 * sizeof(int), stream_), "memset");
+    }
+    if (filt_bp_) {
+        // BandPassFilter::new (band_pass_filter.rs:31-55), f32
+        const float pi = 3.14159265358979323846f, sr = (float)kSampleRate;
+        const float omega_low = 2.0f * pi * cfg.low_cutoff / sr, omega_high = 2.0f * pi * cfg.high_cutoff / sr;
+        const float alpha_low = std::sin(omega_low) / 2.0f, alpha_high = std::sin(omega_high) / 2.0f;
+        const float a0 = 1.0f / (1.0f + alpha_high - alpha_low);
+        bp_[0] = a0;
+        bp_[1] = -2.0f * std::cos(omega_low) * a0;
+        bp_[2] = (1.0f - alpha_high - alpha_low) * a0;
+        bp_[3] = -2.0f * std::cos(omega_high) * a0;
+        bp_[4] = (1.0f - alpha_high + alpha_low) * a0;
+        bp_state_.reserve((size_t)n_streams_ * 4 * sizeof(float), "band-pass state");
+        cuda_check(cudaMemsetAsync(bp_state_.as<void>(), 0, (size_t)n_streams_ * 4 * sizeof(float), stream_), "memset");
+    }
+    cuda_check(cudaStreamSynchronize(stream_), "sync");
+}
+
+void Engine::set_gain_reference(float target_rms_level, int window_size) {
+    if (!filt_fixed_ref_) {
+        filt_ref_ = target_rms_level;
+        filt_ref_sqrt_ = std::sqrt(target_rms_level);
+    }
+    filt_window_ = std::min(window_size != 0 ? window_size : 1, kGainWindowCap - 1);
+}
+
 void Engine::ensure_frames(int n_new) {
     if (n_new <= frames_cap_) return;
     const size_t old_rows = (size_t)hist_ + frames_cap_, rows = (size_t)hist_ + n_new;
@@ -209,8 +250,11 @@ void Engine::process(const float* audio, int64_t S, bool on_device, bool want_va
         vad_.reserve((size_t)n_windows * sizeof(float), "vad values");
         vad_dev = vad_.as<float>();
     }
-    if (!on_device) audio_.reserve((size_t)n_streams_ * S * sizeof(float), "audio staging");
-    const float* src_all = on_device ? audio : audio_.as<float>();
+    const bool filters = filt_gain_ || filt_bp_;
+    if (!on_device || filters) audio_.reserve((size_t)n_streams_ * S * sizeof(float), "audio staging");
+    const float* src_all = (on_device && !filters) ? audio : audio_.as<float>();
+    const int n_chunks = (int)(S / kFrameSamples);
+    if (filt_gain_) gains_.reserve((size_t)n_streams_ * n_chunks * sizeof(float), "gains");
 
     // The batch is processed in groups of streams: group g's kernels wait only for group g's H2D copy,
     // so the copy of group g+1 (copy stream) overlaps the kernels of group g, and a group's frames
@@ -238,6 +282,30 @@ void Engine::process(const float* audio, int64_t S, bool on_device, bool want_va
         const int64_t b0 = g * gs, nb = std::min(gs, n_streams_ - b0);
         if (!on_device) cuda_check(cudaStreamWaitEvent(stream_, group_ev_[4 * g], 0), "wait");
         cuda_check(cudaEventRecord(group_ev_[4 * g + 1], stream_), "event");
+        if (filters) {  // gain normaliser / band pass: caller's (or staged) audio -> staging buffer
+            FilterArgs fa;
+            fa.in = (on_device ? audio : audio_.as<float>()) + b0 * S;
+            fa.in_stride = S;
+            fa.out = audio_.as<float>() + b0 * S;
+            fa.out_stride = S;
+            fa.n_streams = nb;
+            fa.n_chunks = n_chunks;
+            fa.gain = filt_gain_;
+            fa.rms_level_ref = filt_ref_;
+            fa.rms_level_sqrt = filt_ref_sqrt_;
+            fa.min_gain = filt_min_gain_;
+            fa.max_gain = filt_max_gain_;
+            fa.window_size = filt_window_;
+            fa.window_cap = kGainWindowCap;
+            fa.gain_window = filt_gain_ ? gain_window_.as<float>() + b0 * kGainWindowCap : nullptr;
+            fa.gain_count = filt_gain_ ? gain_count_.as<int>() + b0 * 2 : nullptr;
+            fa.gains_out = filt_gain_ ? gains_.as<float>() + b0 * n_chunks : nullptr;
+            fa.band_pass = filt_bp_;
+            fa.a0 = bp_[0]; fa.a1 = bp_[1]; fa.a2 = bp_[2]; fa.b1 = bp_[3]; fa.b2 = bp_[4];
+            fa.bp_state = filt_bp_ ? bp_state_.as<float>() + b0 * 4 : nullptr;
+            cuda_check(launch_audio_filters(fa, stream_), "filter kernel");
+            launches += 1;
+        }
         const float* src = src_all + b0 * S;
         float* fb = fb_all + b0 * rows * d_;
         float* carry = carry_.as<float>() + b0 * 2 * kHopSamples;
@@ -308,6 +376,10 @@ void Engine::process(const float* audio, int64_t S, bool on_device, bool want_va
             hit_host_floats_ = need * 2;
         }
         cuda_check(cudaMemcpyAsync(hit_host_, hits_.as<void>(), need * sizeof(float), cudaMemcpyDeviceToHost, stream_), "D2H hits");
+    }
+    if (filt_gain_) {
+        gains_host_.resize((size_t)n_streams_ * n_chunks);
+        cuda_check(cudaMemcpyAsync(gains_host_.data(), gains_.as<void>(), gains_host_.size() * sizeof(float), cudaMemcpyDeviceToHost, stream_), "D2H gains");
     }
     if (want_vad && vad) {
         vad->resize((size_t)n_windows);

@@ -64,6 +64,14 @@ class Engine {
     // Uploads templates / tables for the wakeword set; keeps per-stream frame history.
     void configure(const WakewordSet& ws, const rp_config& cfg);
     void set_dtw_variant(int v) { dtw_variant_ = v; }
+    // FiltersConfig (src/config.rs:31-84): fresh filter state for every stream (update_filters_config semantics:
+    // the gain reference is NOT re-derived from the wakewords until set_gain_reference is called again).
+    void set_filters(const rp_config& cfg);
+    // GainNormalizerFilter::set_rms_level_ref (gain_normalizer_filter.rs:42-48), on every wakeword change
+    void set_gain_reference(float target_rms_level, int window_size);
+    bool gain_filter_enabled() const { return filt_gain_; }
+    // gains applied per (stream, chunk) by the last process() when the gain normaliser is enabled
+    const std::vector<float>& last_gains() const { return gains_host_; }
 
     // Scores samples_per_stream/160 new hops per stream. Returns the hits sorted by (stream, frame);
     // `vad` (if want_vad) receives [n_streams][n_hops] mean |mfcc| per new frame.
@@ -111,6 +119,14 @@ class Engine {
     DeviceBuffer hits_;        // [cap][5 + max_templates]
     DeviceBuffer hit_count_;   // int
     int last_n_new_ = 0;
+    // audio filters (batched front-end)
+    bool filt_gain_ = false, filt_bp_ = false, filt_fixed_ref_ = false;
+    float filt_ref_ = 0.f, filt_ref_sqrt_ = 0.f, filt_min_gain_ = 0.1f, filt_max_gain_ = 1.f;
+    int filt_window_ = 1;
+    float bp_[5] = {0, 0, 0, 0, 0};
+    static constexpr int kGainWindowCap = 512;
+    DeviceBuffer gain_window_, gain_count_, bp_state_, gains_;
+    std::vector<float> gains_host_;
     // pinned host staging for the hit list
     float* hit_host_ = nullptr;
     size_t hit_host_floats_ = 0;

@@ -83,6 +83,7 @@ cudaError_t launch_dtw_windows_generic(const DtwWindowsArgs& a, cudaStream_t str
 // Tuned variant for d == 16, band == 5 (dtw_window_kernel.cu). tmpl_unit: the templates of a.tmpl with every row
 // scaled to unit length (zero rows stay zero), same offsets.
 cudaError_t launch_dtw_windows_d16(const DtwWindowsArgs& a, const float* tmpl_unit, cudaStream_t stream);
+void set_dtw_window_kernel(int v);  // 0/1 = one window per thread (default), 2 = two windows per thread
 
 // K3: judge every window, append detections to a compact hit list.
 // hit record (floats/ints, stride = 5 + max_templates): [stream, frame, wakeword, avg_score, score, scores...]
@@ -102,6 +103,28 @@ struct JudgeArgs {
     int first_window = 0;              // windows j < first_window are skipped
 };
 cudaError_t launch_judge_windows(const JudgeArgs& a, cudaStream_t stream);
+
+// Audio filters in front of the MFCC kernel (filter_kernel.cu); one lane per stream, chunks of 480 samples.
+struct FilterArgs {
+    const float* in = nullptr;   // [n_streams][in_stride]
+    int64_t in_stride = 0;
+    float* out = nullptr;        // [n_streams][out_stride] (may alias `in`)
+    int64_t out_stride = 0;
+    int64_t n_streams = 0;
+    int n_chunks = 0;
+    // gain normaliser (gain_normalizer_filter.rs)
+    int gain = 0;
+    float rms_level_ref = 0.f, rms_level_sqrt = 0.f, min_gain = 0.1f, max_gain = 1.f;
+    int window_size = 1, window_cap = 1;
+    float* gain_window = nullptr;  // [n_streams][window_cap] rms ring
+    int* gain_count = nullptr;     // [n_streams][2] entries, head
+    float* gains_out = nullptr;    // [n_streams][n_chunks] gain applied to each chunk (nullptr: not recorded)
+    // band pass (band_pass_filter.rs)
+    int band_pass = 0;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
+    float* bp_state = nullptr;     // [n_streams][4] x1 x2 y1 y2
+};
+cudaError_t launch_audio_filters(const FilterArgs& a, cudaStream_t stream);
 
 // misc small kernels
 cudaError_t launch_copy_rows(const float* src, int64_t src_stride, float* dst, int64_t dst_stride, int64_t n_streams,

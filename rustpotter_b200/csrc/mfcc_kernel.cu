@@ -193,10 +193,11 @@ mfcc_frames_kernel(const float* __restrict__ audio, int64_t audio_stride, const 
 
 // =============================================================================================
 // K1 v2 — two frames per warp, TMA-staged samples.
-//   * A CTA (8 warps) produces 16 consecutive frames of one stream. Their 18 hops of samples are
-//     contiguous in HBM and are staged into shared memory by ONE bulk asynchronous copy
-//     (cp.async.bulk -> UBLKCP, completion on an mbarrier); the first CTA of a streaming call adds a second
-//     bulk copy for the two carried hops.
+//   * A CTA (8 warps) produces up to 4 tiles of 16 consecutive frames of one stream. A tile's 18 hops of
+//     samples are contiguous in HBM and are staged into shared memory by ONE bulk asynchronous copy
+//     (cp.async.bulk -> UBLKCP, completion on an mbarrier), double-buffered: tile i+1 is in flight while
+//     tile i is transformed; the first tile of a streaming call adds a second bulk copy for the two
+//     carried hops.
 //   * Warp w packs frame A = 2w (real part) and frame B = 2w+1 (imaginary part) into one complex
 //     480-point FFT (same 15 x 32 factorisation as v1) and separates the two spectra afterwards:
 //     X_A[k] = (Z[k] + conj Z[480-k]) / 2,  X_B[k] = (Z[k] - conj Z[480-k]) / 2i; Z[480-k] lives in lane
@@ -206,8 +207,9 @@ mfcc_frames_kernel(const float* __restrict__ audio, int64_t audio_stride, const 
 //   * DCT: lanes 0..15 produce c1..c16 of frame A, lanes 16..31 those of frame B (reference summation
 //     order, un-fused), so the two frames leave as one coalesced 128-byte store.
 // Requires mfcc_size <= 16 and 16-byte aligned stream rows; otherwise v1 is used.
-constexpr int kFramesPerCta = 16;
-constexpr int kTileHops = kFramesPerCta + 2;
+constexpr int kFramesPerTile = 16;
+constexpr int kTileHops = kFramesPerTile + 2;
+constexpr int kTilesPerCta = 4;     // consecutive tiles of one stream per CTA, double-buffered
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -215,54 +217,69 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 mfcc_frames2_kernel(const float* __restrict__ audio, int64_t audio_stride, const float* __restrict__ carry,
                     int frames_per_stream, int sample_offset0, MfccTablesDev t, float* __restrict__ out,
                     int64_t out_stride_frames, int out_row0, float* __restrict__ vad_out, int ctas_per_stream) {
-    __shared__ __align__(16) float xs[kTileHops * kHop];
+    __shared__ __align__(16) float xs_all[2][kTileHops * kHop];
     __shared__ float pw[kWarpsPerBlock][2][kBins];
     __shared__ float part_s[kWarpsPerBlock][2][32], part_u[kWarpsPerBlock][2][32];
     __shared__ float lbuf[kWarpsPerBlock][2][32];
-    __shared__ __align__(8) unsigned long long bar;
+    __shared__ __align__(8) unsigned long long bars[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t b = blockIdx.x / ctas_per_stream;
-    const int j0 = (int)(blockIdx.x - b * ctas_per_stream) * kFramesPerCta;
-    const int nf = min(kFramesPerCta, frames_per_stream - j0);          // frames of this CTA
-    const int64_t g0 = (int64_t)kHop * j0 + sample_offset0;             // logical sample of xs[0]
-    const int n_samples = (nf + 2) * kHop;
+    const int jcta = (int)(blockIdx.x - b * ctas_per_stream) * (kFramesPerTile * kTilesPerCta);
+    const int n_tiles = min(kTilesPerCta, (frames_per_stream - jcta + kFramesPerTile - 1) / kFramesPerTile);
 
-    // ---- stage the samples: bulk async copy, completion counted in bytes on the mbarrier
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0) {
-        const unsigned bar_a = smem_u32(&bar);
+    // Stages tile `tile` into buffer `stage`: one bulk async copy (two for the first tile of a streaming
+    // call, whose first two hops come from the carry buffer), completion counted in bytes on the mbarrier.
+    auto issue_tile = [&](int tile, int stage) {
+        const int j0 = jcta + tile * kFramesPerTile;
+        const int nf = min(kFramesPerTile, frames_per_stream - j0);
+        const int64_t g0 = (int64_t)kHop * j0 + sample_offset0;   // logical sample of xs[0]
+        const int n_samples = (nf + 2) * kHop;
+        const unsigned bar_a = smem_u32(&bars[stage]);
+        float* dst = xs_all[stage];
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(n_samples * 4) : "memory");
         int from_carry = 0;
-        if (g0 < 0) {  // the two hops kept from the previous call
+        if (g0 < 0) {
             from_carry = (int)(-g0);
             const float* src = carry + b * (2 * kHop) + (2 * kHop - from_carry);
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32(xs)), "l"(src), "r"(from_carry * 4), "r"(bar_a) : "memory");
+                         ::"r"(smem_u32(dst)), "l"(src), "r"(from_carry * 4), "r"(bar_a) : "memory");
         }
         const float* src = audio + b * audio_stride + (g0 < 0 ? 0 : g0);
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(xs + from_carry)), "l"(src), "r"((n_samples - from_carry) * 4), "r"(bar_a) : "memory");
+                     ::"r"(smem_u32(dst + from_carry)), "l"(src), "r"((n_samples - from_carry) * 4), "r"(bar_a) : "memory");
+    };
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    {   // every thread waits for phase 0 of the barrier
-        const unsigned bar_a = smem_u32(&bar);
+    __syncthreads();
+    if (tid == 0) issue_tile(0, 0);
+
+    for (int tile = 0; tile < n_tiles; tile++) {
+    const int stage = tile & 1;
+    // prefetch the next tile into the other buffer (its last readers passed the __syncthreads below)
+    if (tid == 0 && tile + 1 < n_tiles) issue_tile(tile + 1, stage ^ 1);
+    {   // wait for this tile: the barrier of a stage completes once per use -> parity (tile / 2) & 1
+        const unsigned bar_a = smem_u32(&bars[stage]);
+        const unsigned parity = (tile >> 1) & 1;
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
             "WAIT_LOOP:\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
             "@p bra WAIT_DONE;\n"
             "bra WAIT_LOOP;\n"
             "WAIT_DONE:\n"
-            "}\n" ::"r"(bar_a) : "memory");
+            "}\n" ::"r"(bar_a), "r"(parity) : "memory");
     }
-
-    const int fa = 2 * warp;            // frame A of this warp inside the CTA (frame B = fa + 1)
-    if (fa >= nf) return;
+    const float* xs = xs_all[stage];
+    const int j0 = jcta + tile * kFramesPerTile;
+    const int nf = min(kFramesPerTile, frames_per_stream - j0);
+    const int fa = 2 * warp;            // frame A of this warp inside the tile (frame B = fa + 1)
+    if (fa < nf) {
     const bool has_b = fa + 1 < nf;
     const int n2 = (int)(__brev((unsigned)lane) >> 27);
     const int C = t.num_coefficients, D = C - 1;
@@ -286,12 +303,12 @@ mfcc_frames2_kernel(const float* __restrict__ audio, int64_t audio_stride, const
             const int s = 32 * i + n2;
             const float h = __ldg(t.hamming + s);
             const bool second = pass == 0 && has_b;      // imaginary slot <- frame B
-            const float x0 = xp[s], x1 = second ? xp[s + kHop] : 0.f;
-            float y0 = x0, y1 = x1;
-            if (s % kHop != 0) {
-                y0 = __fsub_rn(x0, __fmul_rn(kPre, xp[s - 1]));
-                y1 = second ? __fsub_rn(x1, __fmul_rn(kPre, xp[s + kHop - 1])) : 0.f;
-            }
+            // y = x[s] - 0.97 * x[s-1], restarting at every hop (s % 160 == 0 happens only for n2 == 0): the
+            // coefficient is 0 there, which keeps the arithmetic identical (x - 0*prev == x) without a branch
+            const float coef = (s % kHop != 0) ? kPre : 0.f;
+            const int sp = s > 0 ? s - 1 : 0;
+            const float y0 = __fsub_rn(xp[s], __fmul_rn(coef, xp[sp]));
+            const float y1 = second ? __fsub_rn(xp[s + kHop], __fmul_rn(coef, xp[sp + kHop])) : 0.f;
             xr[i] = __fmul_rn(y0, h);
             xi[i] = __fmul_rn(y1, h);
         }
@@ -359,30 +376,34 @@ mfcc_frames2_kernel(const float* __restrict__ audio, int64_t audio_stride, const
             re[k] = r;
             im[k] = q;
         }
-        // ---- 32-point DIT FFT across lanes (lane k2 ends with Z[k1 + 15*k2])
+        // ---- 32-point DIT FFT across lanes (lane k2 ends with Z[k1 + 15*k2]).
+        // Butterfly X_top = A + wB, X_bot = A - wB without selects: every lane first scales its own value by
+        // its stage factor (w on "bottom" lanes, 1 on "top" lanes), the pair swaps, and each lane finishes
+        // with one signed FMA: top = own + other, bottom = other - own.
         {
-            const bool bottom = lane & 1;
+            const float sgn = (lane & 1) ? -1.f : 1.f;
 #pragma unroll
             for (int k = 0; k < 15; k++) {
                 const float orr = __shfl_xor_sync(0xffffffffu, re[k], 1);
                 const float oi = __shfl_xor_sync(0xffffffffu, im[k], 1);
-                re[k] = bottom ? orr - re[k] : re[k] + orr;
-                im[k] = bottom ? oi - im[k] : im[k] + oi;
+                re[k] = fmaf(sgn, re[k], orr);
+                im[k] = fmaf(sgn, im[k], oi);
             }
         }
 #pragma unroll
         for (int h = 2; h <= 16; h <<= 1) {
             const bool bottom = (lane & h) != 0;
             float2 w = __ldg(t.tw480 + (lane & (h - 1)) * (kBins / h));
-            if (bottom) { w.x = -w.x; w.y = -w.y; }
+            if (!bottom) w = make_float2(1.f, 0.f);
+            const float sgn = bottom ? -1.f : 1.f;
 #pragma unroll
             for (int k = 0; k < 15; k++) {
-                const float orr = __shfl_xor_sync(0xffffffffu, re[k], h);
-                const float oi = __shfl_xor_sync(0xffffffffu, im[k], h);
-                const float ar = bottom ? orr : re[k], ai = bottom ? oi : im[k];
-                const float br = bottom ? re[k] : orr, bi = bottom ? im[k] : oi;
-                re[k] = ar + (br * w.x - bi * w.y);
-                im[k] = ai + (br * w.y + bi * w.x);
+                const float vr = re[k] * w.x - im[k] * w.y;
+                const float vi = re[k] * w.y + im[k] * w.x;
+                const float orr = __shfl_xor_sync(0xffffffffu, vr, h);
+                const float oi = __shfl_xor_sync(0xffffffffu, vi, h);
+                re[k] = fmaf(sgn, vr, orr);
+                im[k] = fmaf(sgn, vi, oi);
             }
         }
         // ---- separate the two spectra and take |X|^2 for bins < 240 (lanes 0..15)
@@ -457,6 +478,9 @@ mfcc_frames2_kernel(const float* __restrict__ audio, int64_t audio_stride, const
         if (lane == 0) vad_out[b * frames_per_stream + j0 + fa] = __fdiv_rn(s0, (float)D);
         if (lane == 16 && has_b) vad_out[b * frames_per_stream + j0 + fa + 1] = __fdiv_rn(s1, (float)D);
     }
+    }  // fa < nf
+    __syncthreads();  // every warp is done with xs_all[stage] before it is refilled
+    }  // tiles
 }
 
 __global__ void copy_rows_kernel(const float* __restrict__ src, int64_t src_stride, float* __restrict__ dst,
@@ -481,7 +505,7 @@ cudaError_t launch_mfcc_frames(const float* audio, int64_t audio_stride, const f
     const bool aligned = (audio_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(audio) & 15) == 0) &&
                          (carry == nullptr || (reinterpret_cast<uintptr_t>(carry) & 15) == 0);
     if (g_mfcc_variant != 1 && t.num_coefficients - 1 <= 16 && t.n_chunks > 0 && aligned && sample_offset0 % 4 == 0) {
-        const int ctas_per_stream = (frames_per_stream + kFramesPerCta - 1) / kFramesPerCta;
+        const int ctas_per_stream = (frames_per_stream + kFramesPerTile * kTilesPerCta - 1) / (kFramesPerTile * kTilesPerCta);
         const int64_t ctas = n_streams * (int64_t)ctas_per_stream;
         if (ctas <= 0x7fffffffLL) {
             mfcc_frames2_kernel<<<(unsigned)ctas, kWarpsPerBlock * 32, 0, stream>>>(
