@@ -85,7 +85,7 @@ __device__ __forceinline__ float dot16(const Row16& a, const Row16& b) {
 }
 
 template <int W>
-__global__ void __launch_bounds__(kThreads) dtw_windows_d16_kernel(DtwWindowsArgs a, const float* __restrict__ tmpl_unit,
+__global__ void __launch_bounds__(kThreads, 5) dtw_windows_d16_kernel(DtwWindowsArgs a, const float* __restrict__ tmpl_unit,
                                                                    int x_rows, int j_blocks) {
     constexpr int NB = 2 * W;  // band cells per row
     extern __shared__ __align__(16) float sm[];
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kThreads) dtw_windows_d16_kernel(DtwWindowsArg
     float* Os = Gs + 2 * GS;                     // [kThreads/16 + 1][16] segment offsets of the row prefix (16 B aligned)
     const int p_rows = kNW + a.max_len + 1;      // prefix rows 0 .. kNW + m
     const int SEG = (p_rows + kThreads / 16 - 1) / (kThreads / 16);  // rows per prefix segment
-    float* Ps = Os + (kThreads / 16 + 1) * kD;   // [p_rows][kXS] exclusive row prefix sums within SEG-row segments
+    float* Ps = Os + (kThreads / 16 + 1) * kD;   // [p_rows][16] exclusive row prefix sums within SEG-row segments
 
     const int tid = threadIdx.x;
     const int64_t cta = blockIdx.x;
@@ -123,7 +123,10 @@ __global__ void __launch_bounds__(kThreads) dtw_windows_d16_kernel(DtwWindowsArg
     }
     __syncthreads();
 
-    const bool dp = tid < kNW;                 // DP thread (one window) vs helper warp
+    // DP thread (one window) vs helper warp; a DP warp whose 32 windows all lie beyond n_new (tail block) only
+    // keeps the barriers company: nothing it would produce is read by a live window (G_r[u] of thread t is
+    // consumed by threads t..t+2W-1 only)
+    const bool dp = tid < kNW && (j0 + (tid & ~31)) < a.n_new;
     const int t = dp ? tid : 0;
     const bool live = dp && (j0 + tid) < a.n_new;
 
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(kThreads) dtw_windows_d16_kernel(DtwWindowsArg
         for (int i = 0; i < SEG; i++) {
             const int u = seg * SEG + i;
             if (u < p_rows) {
-                Ps[u * kXS + dd] = run;
+                Ps[u * kD + dd] = run;
                 if (u < x_rows) run += Xs[u * kXS + dd];
             }
         }
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(kThreads) dtw_windows_d16_kernel(DtwWindowsArg
     f2 nmu[8];  // NEGATED mean, packed
     {
         const int u0 = t, u1 = t + m;
-        const Row16 p0 = lds_row(Ps + u0 * kXS), p1 = lds_row(Ps + u1 * kXS);
+        const Row16 p0 = lds_row(Ps + u0 * kD), p1 = lds_row(Ps + u1 * kD);
         const Row16 o0 = lds_row(Os + (u0 / SEG) * kD), o1 = lds_row(Os + (u1 / SEG) * kD);
         const float fm = (float)m;
 #pragma unroll
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(kThreads) dtw_windows_d16_kernel(DtwWindowsArg
                     inv[(k + W) % NB] = n2 > 0.f ? rsqrtf(n2) : 0.f;  // column r+W-1 = (k+1)+W-1 mod NB
                     G[t + NB - 1] = hsum(g);
                     A = -hsum(aa);                                     // a^_r . mu  (nmu is negated)
-                } else if (tid - kNW < NB - 1) {
+                } else if (tid >= kNW && tid - kNW < NB - 1) {
                     // helper warp: the NB-1 lowest frames of this row's shared range
                     const int e = tid - kNW;
                     const int u = r - W - 1 + e;
@@ -510,7 +513,7 @@ cudaError_t launch_dtw_windows_d16(const DtwWindowsArgs& a, const float* tmpl_un
         return cudaGetLastError();
     }
     const size_t bytes = ((size_t)x_rows * kXS + (size_t)a.max_len * kD + 2 * (kNW + 2 * W) + (kThreads / 16 + 1) * kD +
-                          (size_t)p_rows * kXS) * sizeof(float);
+                          (size_t)p_rows * kD) * sizeof(float);
     if (bytes > 200 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(dtw_windows_d16_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
