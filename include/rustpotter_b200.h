@@ -170,6 +170,21 @@ int rp_batch_last_launches(const rp_batch* b);
 int64_t rp_batch_copy_last_scores(const rp_batch* b, float* out_host, int64_t cap_floats, int32_t* n_new, int32_t* n_slots);
 
 /* =============================================================================================
+ * Wakeword-reference builder: the producer of the templates the hot path scores.
+ * ============================================================================================= */
+/* WakewordRef::new_from_sample_buffers (rms_median == 0: rms_level = max over samples) /
+ * new_from_sample_files (rms_median != 0: rms_level = median over samples) followed by
+ * WakewordSave::save_to_buffer — reference src/wakewords/comp/wakeword_ref_build.rs:9-110,
+ * src/mfcc/wav_file_extractor.rs:18-91, src/mfcc/averager.rs:5-37, src/wakewords/wakeword_file.rs:10-26.
+ * wavs[i] / wav_lens[i]: whole 16 kHz WAV files (PCM int 8/16/32 or float 32, any channel count; other
+ * rates need the reference's rubato resampler, which is outside this path -> RP_ERR_UNSUPPORTED).
+ * MFCCs are extracted by K1 on CUDA device `device`; averaging and CBOR encoding run on the host.
+ * Writes the .rpw bytes to out (out may be NULL to query) and returns their size, or <0. */
+int64_t rp_wakeword_build(const char* name, int has_threshold, float threshold, int has_avg_threshold, float avg_threshold,
+                          int n_samples, const char* const* sample_names, const uint8_t* const* wavs, const size_t* wav_lens,
+                          int mfcc_size, int rms_median, int device, uint8_t* out, size_t out_cap);
+
+/* =============================================================================================
  * Raw kernels (micro-benchmarks, parity tests). All pointers are DEVICE pointers.
  * ============================================================================================= */
 /* K1 — MfccExtractor::compute over whole streams (extractor.rs:60-163): a fresh extractor fed
@@ -213,6 +228,15 @@ int rp_wakeword_inspect(const uint8_t* buf, size_t len, rp_wakeword_info* info);
 /* Copies template t (t == -1: avg_features) of a .rpw buffer: name (RP_NAME_MAX bytes) and
  * row-major [frames][mfcc_size] floats; returns frames or <0. out may be NULL to query. */
 int rp_wakeword_template(const uint8_t* buf, size_t len, int t, char* name_out, float* out, size_t out_cap_floats);
+/* WakewordRef::compute_avg_samples_features + WakewordRef::new + save_to_buffer
+ * (wakeword_ref_build.rs:93-110, wakeword_ref.rs:43-66, averager.rs:5-37) from already extracted and
+ * normalised template matrices: data[t] is row-major [frames[t]][mfcc_size]. The host half of
+ * rp_wakeword_build, exposed so the averager and the CBOR writer can be tested without a GPU.
+ * Returns the .rpw size (out may be NULL to query) or <0. */
+int64_t rp_wakeword_from_features(const char* name, int has_threshold, float threshold, int has_avg_threshold,
+                                  float avg_threshold, int mfcc_size, int n_templates, const char* const* names,
+                                  const int32_t* frames, const float* const* data, float rms_level,
+                                  uint8_t* out, size_t out_cap);
 /* Replays the per-stream state machine of detector.rs:377-454 over a dense score tensor as the
  * kernels produce it. scores: [n_frames][n_slots] where frame i is the i-th frame the extractor
  * emits for a fresh stream (hop i+3) and slots are, per wakeword in insertion order,

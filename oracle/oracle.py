@@ -145,6 +145,10 @@ def lib(native: bool = False) -> C.CDLL:
     L.rpo_wakeword_encode.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int32),
                                       C.POINTER(f32p), C.c_int, f32p, C.c_float, C.c_int, C.c_float, C.c_int, C.c_float,
                                       C.c_int, C.c_char_p, C.c_size_t]
+    L.rpo_wakeword_build.restype = C.c_size_t
+    L.rpo_wakeword_build.argtypes = [C.c_char_p, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, C.POINTER(C.c_char_p),
+                                     C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_char_p, C.c_size_t,
+                                     C.c_char_p, C.c_size_t]
     L.rpo_detector_new.restype = C.c_void_p
     L.rpo_detector_new.argtypes = [C.POINTER(Config), C.c_char_p, C.c_size_t]
     L.rpo_detector_free.argtypes = [C.c_void_p]
@@ -316,6 +320,23 @@ def encode_wakeword(name, templates, avg=None, rms_level=0.05, threshold=None, a
     out = C.create_string_buffer(n)
     lib().rpo_wakeword_encode(*args, out, n)
     return out.raw
+
+
+def build_wakeword(name: str, samples: list[tuple[str, bytes]], mfcc_size: int, threshold=None, avg_threshold=None,
+                   from_files: bool = True) -> bytes:
+    """WakewordRef::new_from_sample_files / _buffers + save_to_buffer. samples: [(file name, wav bytes)]."""
+    names = (C.c_char_p * len(samples))(*[n.encode() for n, _ in samples])
+    bufs = (C.c_char_p * len(samples))(*[b for _, b in samples])
+    lens = (C.c_size_t * len(samples))(*[len(b) for _, b in samples])
+    cap = 64 + sum(len(b) for _, b in samples) * 4
+    out = C.create_string_buffer(cap)
+    err = C.create_string_buffer(256)
+    n = lib().rpo_wakeword_build(name.encode(), int(threshold is not None), float(threshold or 0), int(avg_threshold is not None),
+                                 float(avg_threshold or 0), len(samples), names, bufs, lens, mfcc_size, int(from_files), out, cap,
+                                 err, 256)
+    if n == 0:
+        raise ValueError(err.value.decode())
+    return out.raw[:n]
 
 
 # ---------------------------------------------------------------- detector

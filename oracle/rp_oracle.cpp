@@ -996,6 +996,115 @@ struct Rustpotter {
     }
 };
 
+// ------------------------------------------------------------------------------------------
+// WAV decoding as hound 3.5 + AudioEncoder see it (src/mfcc/wav_file_extractor.rs:18-112): PCM
+// int 8/16/32 or IEEE float 32, little endian; 8-bit WAV is unsigned on disk and signed in hound.
+// ------------------------------------------------------------------------------------------
+struct WavData {
+    uint32_t sample_rate = 0;
+    uint16_t channels = 0, bits = 0;
+    bool is_float = false;
+    std::vector<float> f32;  // every interleaved sample after Sample::into_f32 (audio_types.rs:98-137)
+};
+static bool parse_wav(const uint8_t* b, size_t len, WavData& w, std::string& err) {
+    auto u16 = [&](size_t o) { return (uint16_t)(b[o] | b[o + 1] << 8); };
+    auto u32 = [&](size_t o) { return (uint32_t)b[o] | (uint32_t)b[o + 1] << 8 | (uint32_t)b[o + 2] << 16 | (uint32_t)b[o + 3] << 24; };
+    if (len < 12 || std::memcmp(b, "RIFF", 4) || std::memcmp(b + 8, "WAVE", 4)) { err = "no RIFF tag found"; return false; }
+    size_t off = 12;
+    bool have_fmt = false;
+    uint16_t tag = 0;
+    while (off + 8 <= len) {
+        uint32_t sz = u32(off + 4);
+        size_t body = off + 8;
+        if (!std::memcmp(b + off, "fmt ", 4) && body + 16 <= len) {
+            tag = u16(body);
+            w.channels = u16(body + 2);
+            w.sample_rate = u32(body + 4);
+            w.bits = u16(body + 14);
+            if (tag == 0xfffe && body + 26 <= len) tag = u16(body + 24);  // WAVE_FORMAT_EXTENSIBLE sub-format
+            have_fmt = true;
+        } else if (!std::memcmp(b + off, "data", 4)) {
+            if (!have_fmt) { err = "data chunk before fmt chunk"; return false; }
+            size_t n = std::min<size_t>(sz, len - body);
+            w.is_float = tag == 3;
+            // TryFrom<WavSpec> for AudioFmt (wav_file_extractor.rs:93-112)
+            bool ok = w.is_float ? w.bits == 32 : (w.bits == 8 || w.bits == 16 || w.bits == 32);
+            if (!ok || (tag != 1 && tag != 3)) { err = "Unsupported wav format"; return false; }
+            size_t bs = w.bits / 8, cnt = n / bs;
+            w.f32.resize(cnt);
+            for (size_t i = 0; i < cnt; i++) {
+                const uint8_t* p = b + body + i * bs;
+                if (w.is_float) { std::memcpy(&w.f32[i], p, 4); }
+                else if (w.bits == 8) w.f32[i] = (float)(int8_t)(p[0] - 128) / 127.f;
+                else if (w.bits == 16) w.f32[i] = (float)(int16_t)(p[0] | p[1] << 8) / 32767.f;
+                else w.f32[i] = (float)(int32_t)((uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24) / (float)2147483647;
+            }
+            return true;
+        }
+        off = body + sz + (sz & 1);
+    }
+    err = "no data chunk";
+    return false;
+}
+
+// MfccWavFileExtractor::compute_mfccs (wav_file_extractor.rs:18-68)
+static bool wav_mfccs(const uint8_t* b, size_t len, uint16_t mfcc_size, Mat& out, float& rms_level, std::string& err) {
+    WavData w;
+    if (!parse_wav(b, len, w, err)) return false;
+    if (w.sample_rate != SAMPLE_RATE) { err = "oracle: resampler (rubato) not restated; wav sample rate must be 16000"; return false; }
+    const size_t in_frame = (SAMPLE_RATE * FRAME_LENGTH_MS / 1000) * w.channels;  // encoder.rs:68-69
+    MfccExtractor ex(SAMPLE_RATE, 480, 160, (uint16_t)(mfcc_size + 1), PRE_EMPHASIS);
+    Vec rms_levels;
+    Vec encoded;
+    for (size_t off = 0; off + in_frame <= w.f32.size(); off += in_frame) {  // chunks_exact
+        Vec mono;
+        for (size_t i = 0; i < in_frame; i += w.channels) mono.push_back(w.f32[off + i]);
+        rms_levels.push_back(GainNormalizerFilter::get_rms_level(mono));
+        encoded.insert(encoded.end(), mono.begin(), mono.end());
+    }
+    if (!rms_levels.empty()) {
+        std::sort(rms_levels.begin(), rms_levels.end(), total_less);
+        rms_level = rms_levels[rms_levels.size() / 2];
+    }
+    Mat frames;
+    for (size_t off = 0; off + 480 <= encoded.size(); off += 480) {
+        Mat part = ex.compute(encoded.data() + off, 480);
+        for (auto& f : part) frames.push_back(std::move(f));
+    }
+    out = normalize(frames);
+    return true;
+}
+
+// MfccAverager::average (src/mfcc/averager.rs:5-37) over compute_avg_samples_features' ordering
+// (wakeword_ref_build.rs:90-110): longest first, ties by name.
+static std::optional<Mat> compute_avg_samples_features(const std::vector<std::pair<std::string, Mat>>& templates) {
+    if (templates.size() <= 1) return std::nullopt;
+    std::vector<const std::pair<std::string, Mat>*> order;
+    for (auto& t : templates) order.push_back(&t);
+    std::stable_sort(order.begin(), order.end(), [](auto* a, auto* b) {
+        if (a->second.size() != b->second.size()) return a->second.size() > b->second.size();
+        return a->first < b->first;
+    });
+    Mat origin = order[0]->second;
+    for (size_t k = 1; k < order.size(); k++) {
+        const Mat& frames = order[k]->second;
+        DtwFull dtw;
+        dtw.compute(origin, frames);
+        std::vector<std::vector<Vec>> avgs(origin.size());
+        for (size_t x = 0; x < origin.size(); x++)
+            for (float y : origin[x]) avgs[x].push_back(Vec{y});
+        for (auto& xy : dtw.path())
+            for (size_t idx = 0; idx < frames[xy.second].size(); idx++) avgs[xy.first][idx].push_back(frames[xy.second][idx]);
+        for (size_t x = 0; x < origin.size(); x++)
+            for (size_t idx = 0; idx < origin[x].size(); idx++) {
+                float sum = 0.f;
+                for (float v : avgs[x][idx]) sum += v;
+                origin[x][idx] = sum / (float)avgs[x][idx].size();
+            }
+    }
+    return origin;
+}
+
 static Mat to_mat(const float* p, int rows, int d) {
     Mat m(rows, Vec(d));
     for (int i = 0; i < rows; i++) std::memcpy(m[i].data(), p + (size_t)i * d, sizeof(float) * d);
@@ -1143,6 +1252,49 @@ size_t rpo_wakeword_encode(const char* name, int mfcc_size, int n_templates, con
     else { w.text("mfcc_size"); w.head(0, mfcc_size); }
     if (out && out_cap >= w.b.size()) std::memcpy(out, w.b.data(), w.b.size());
     return w.b.size();
+}
+
+size_t rpo_wakeword_build(const char* name, int has_thr, float thr, int has_avg_thr, float avg_thr, int n_samples,
+                          const char* const* sample_names, const uint8_t* const* wavs, const size_t* wav_lens, int mfcc_size,
+                          int from_files, uint8_t* out, size_t out_cap, char* err, size_t err_len) {
+    // WakewordRefBuildFrom{Files,Buffers} (wakeword_ref_build.rs:9-88)
+    std::vector<std::pair<std::string, Mat>> feats;
+    Vec rms_levels;
+    float rms_max = 0.f;
+    for (int i = 0; i < n_samples; i++) {
+        Mat m;
+        float r = 0.f;
+        std::string e;
+        if (!wav_mfccs(wavs[i], wav_lens[i], (uint16_t)mfcc_size, m, r, e)) { set_err(err, err_len, e); return 0; }
+        if (m.empty()) { set_err(err, err_len, "sample too short"); return 0; }
+        feats.emplace_back(sample_names[i], std::move(m));
+        rms_levels.push_back(r);
+        if (r > rms_max) rms_max = r;
+    }
+    if (feats.empty()) { set_err(err, err_len, "Can not create an empty wakeword"); return 0; }
+    float rms_level = rms_max;
+    if (from_files) {
+        std::sort(rms_levels.begin(), rms_levels.end(), total_less);
+        rms_level = rms_levels[rms_levels.size() / 2];
+    }
+    std::optional<Mat> avg = compute_avg_samples_features(feats);
+    const int d = (int)feats[0].second[0].size();
+    std::vector<Vec> flat;
+    std::vector<const char*> names;
+    std::vector<int32_t> frames;
+    std::vector<const float*> data;
+    for (auto& kv : feats) {
+        Vec f;
+        for (auto& row : kv.second) f.insert(f.end(), row.begin(), row.end());
+        flat.push_back(std::move(f));
+        names.push_back(kv.first.c_str());
+        frames.push_back((int32_t)kv.second.size());
+    }
+    for (auto& f : flat) data.push_back(f.data());
+    Vec avg_flat;
+    if (avg) for (auto& row : *avg) avg_flat.insert(avg_flat.end(), row.begin(), row.end());
+    return rpo_wakeword_encode(name, d, (int)feats.size(), names.data(), frames.data(), data.data(), avg ? (int)avg->size() : 0,
+                               avg ? avg_flat.data() : nullptr, rms_level, has_thr, thr, has_avg_thr, avg_thr, 0, out, out_cap);
 }
 
 rpo_detector* rpo_detector_new(const rpo_config* cfg, char* err, size_t err_len) {

@@ -111,6 +111,14 @@ size_t rpo_wakeword_encode(const char* name, int mfcc_size, int n_templates, con
                            int has_thr, float thr, int has_avg_thr, float avg_thr, int v2,
                            uint8_t* out, size_t out_cap);
 
+/* WakewordRef::new_from_sample_files (from_files != 0: rms_level = median over samples) /
+ * new_from_sample_buffers (rms_level = max) — src/wakewords/comp/wakeword_ref_build.rs:9-110, with
+ * MfccWavFileExtractor (wav_file_extractor.rs:18-91) and MfccAverager (averager.rs:5-37). `wavs` are whole
+ * WAV files (16 kHz). Writes the .rpw CBOR; returns its size (0 + err on failure). */
+size_t rpo_wakeword_build(const char* name, int has_thr, float thr, int has_avg_thr, float avg_thr, int n_samples,
+                          const char* const* sample_names, const uint8_t* const* wavs, const size_t* wav_lens, int mfcc_size,
+                          int from_files, uint8_t* out, size_t out_cap, char* err, size_t err_len);
+
 /* ---- Detector (src/detector.rs) ---- */
 typedef struct rpo_detector rpo_detector;
 rpo_detector* rpo_detector_new(const rpo_config* cfg, char* err, size_t err_len);

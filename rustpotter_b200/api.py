@@ -85,7 +85,7 @@ EXPORTED = [
     "rp_batch_set_cuda_stream", "rp_batch_process", "rp_batch_update_config", "rp_batch_reset",
     "rp_batch_windows_scored", "rp_batch_n_streams", "rp_batch_max_mfcc_frames", "rp_batch_last_timings",
     "rp_batch_last_launches", "rp_batch_copy_last_scores", "rp_mfcc_frames", "rp_dtw_scores", "rp_set_dtw_variant", "rp_set_mfcc_variant", "rp_wakeword_inspect",
-    "rp_wakeword_template", "rp_host_replay",
+    "rp_wakeword_template", "rp_host_replay", "rp_wakeword_build", "rp_wakeword_from_features",
 ]
 
 
@@ -389,6 +389,27 @@ def set_mfcc_variant(v: int):
     lib().rp_set_mfcc_variant(v)
 
 
+# ---------------------------------------------------------------- wakeword builder
+def build_wakeword(name: str, samples: list[tuple[str, bytes]], mfcc_size: int = 16, threshold: float | None = None,
+                   avg_threshold: float | None = None, from_files: bool = True, device: int = 0) -> bytes:
+    """`WakewordRef::new_from_sample_files` (from_files: rms_level = median over the samples) or
+    `new_from_sample_buffers` (max) + `save_to_buffer` (reference wakeword_ref_build.rs:9-110).
+    samples: [(sample name, whole 16 kHz WAV file bytes)]. Returns the .rpw bytes."""
+    L = lib()
+    L.rp_wakeword_build.restype = C.c_int64
+    L.rp_wakeword_build.argtypes = [C.c_char_p, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, C.POINTER(C.c_char_p),
+                                    C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    names = (C.c_char_p * len(samples))(*[n.encode() for n, _ in samples])
+    bufs = (C.c_char_p * len(samples))(*[b for _, b in samples])
+    lens = (C.c_size_t * len(samples))(*[len(b) for _, b in samples])
+    args = (name.encode(), int(threshold is not None), float(threshold or 0.0), int(avg_threshold is not None),
+            float(avg_threshold or 0.0), len(samples), names, bufs, lens, mfcc_size, int(from_files), device)
+    n = _check(L.rp_wakeword_build(*args, None, 0))
+    out = C.create_string_buffer(n)
+    _check(L.rp_wakeword_build(*args, out, n))
+    return out.raw[:n]
+
+
 # ---------------------------------------------------------------- host-logic hooks (no GPU)
 def wakeword_inspect(buf: bytes) -> dict:
     info = WakewordInfo()
@@ -404,6 +425,28 @@ def wakeword_template(buf: bytes, t: int, mfcc_size: int):
     out = np.zeros((rows, mfcc_size), np.float32)
     _check(lib().rp_wakeword_template(buf, len(buf), t, name, out.ctypes.data_as(C.POINTER(C.c_float)), out.size))
     return name.value.decode(), out
+
+
+def wakeword_from_features(name: str, templates: list[tuple[str, "np.ndarray"]], rms_level: float, threshold: float | None = None,
+                           avg_threshold: float | None = None) -> bytes:
+    """Averages already normalised template matrices (MfccAverager) and serialises the WakewordRef."""
+    L = lib()
+    L.rp_wakeword_from_features.restype = C.c_int64
+    FP = C.POINTER(C.c_float)
+    L.rp_wakeword_from_features.argtypes = [C.c_char_p, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, C.c_int,
+                                            C.POINTER(C.c_char_p), C.POINTER(C.c_int32), C.POINTER(FP), C.c_float,
+                                            C.c_void_p, C.c_size_t]
+    mats = [np.ascontiguousarray(m, np.float32) for _, m in templates]
+    d = mats[0].shape[1] if mats else 1
+    names = (C.c_char_p * len(mats))(*[n.encode() for n, _ in templates])
+    frames = (C.c_int32 * len(mats))(*[m.shape[0] for m in mats])
+    data = (FP * len(mats))(*[m.ctypes.data_as(FP) for m in mats])
+    args = (name.encode(), int(threshold is not None), float(threshold or 0.0), int(avg_threshold is not None),
+            float(avg_threshold or 0.0), d, len(mats), names, frames, data, float(rms_level))
+    n = _check(L.rp_wakeword_from_features(*args, None, 0))
+    out = C.create_string_buffer(n)
+    _check(L.rp_wakeword_from_features(*args, out, n))
+    return out.raw[:n]
 
 
 def host_replay(config: Config, rpws: list[bytes], scores, vad_values=None, max_out: int = 64):

@@ -11,6 +11,7 @@
 
 #include "audio_frontend.h"
 #include "detector_core.h"
+#include "wakeword_builder.h"
 #include "engine.h"
 #include "kernels.h"
 #include "mfcc_tables.h"
@@ -370,6 +371,87 @@ int64_t rp_batch_copy_last_scores(const rp_batch* b, float* out, int64_t cap, in
         }
         return (int)std::min<int64_t>(n, 0x7fffffff);
     });
+}
+
+// ------------------------------------------------------------------ wakeword builder
+int64_t rp_wakeword_build(const char* name, int has_threshold, float threshold, int has_avg_threshold, float avg_threshold,
+                          int n_samples, const char* const* sample_names, const uint8_t* const* wavs, const size_t* wav_lens,
+                          int mfcc_size, int rms_median, int device, uint8_t* out, size_t out_cap) {
+    int64_t written = 0;
+    const int rc = guarded((rp_handle*)nullptr, [&] {
+        if (!name || n_samples < 0 || (n_samples > 0 && (!sample_names || !wavs || !wav_lens)))
+            throw Error(RP_ERR_INVALID, "bad argument");
+        std::vector<std::pair<std::string, std::pair<const uint8_t*, size_t>>> samples;
+        for (int i = 0; i < n_samples; i++) {
+            if (!sample_names[i] || !wavs[i]) throw Error(RP_ERR_INVALID, "null sample");
+            samples.push_back({sample_names[i], {wavs[i], wav_lens[i]}});
+        }
+        // MFCC extraction of one sample file = one stream through the K1 kernel
+        MfccFn mfcc = [device](const std::vector<float>& mono, int size) {
+            FrameMatrix f;
+            f.cols = size;
+            const int64_t hops = (int64_t)mono.size() / kHopSamples;
+            if (hops <= 3) return f;
+            cuda_check(cudaSetDevice(device), "cudaSetDevice");
+            const MfccTablesDev& t = tables_for(device, size, nullptr);
+            DeviceBuffer audio, frames;
+            audio.reserve(mono.size() * sizeof(float), "builder audio");
+            f.rows = (int)(hops - 3);
+            f.v.resize((size_t)f.rows * size);
+            frames.reserve(f.v.size() * sizeof(float), "builder frames");
+            cuda_check(cudaMemcpy(audio.as<float>(), mono.data(), mono.size() * sizeof(float), cudaMemcpyHostToDevice), "H2D sample");
+            cuda_check(launch_mfcc_frames(audio.as<float>(), (int64_t)mono.size(), nullptr, 1, f.rows, kHopSamples, t,
+                                          frames.as<float>(), f.rows, 0, nullptr, nullptr), "mfcc kernel");
+            cuda_check(cudaMemcpy(f.v.data(), frames.as<float>(), f.v.size() * sizeof(float), cudaMemcpyDeviceToHost), "D2H frames");
+            return f;
+        };
+        const WakewordRefData w = build_wakeword_ref(name, has_threshold ? std::optional<float>(threshold) : std::nullopt,
+                                                     has_avg_threshold ? std::optional<float>(avg_threshold) : std::nullopt,
+                                                     samples, mfcc_size, rms_median != 0, mfcc);
+        const std::vector<uint8_t> bytes = encode_wakeword_ref(w);
+        written = (int64_t)bytes.size();
+        if (out) {
+            if (bytes.size() > out_cap) throw Error(RP_ERR_INVALID, "output buffer too small");
+            std::memcpy(out, bytes.data(), bytes.size());
+        }
+        return RP_OK;
+    });
+    return rc < 0 ? rc : written;
+}
+
+int64_t rp_wakeword_from_features(const char* name, int has_threshold, float threshold, int has_avg_threshold,
+                                  float avg_threshold, int mfcc_size, int n_templates, const char* const* names,
+                                  const int32_t* frames, const float* const* data, float rms_level,
+                                  uint8_t* out, size_t out_cap) {
+    int64_t written = 0;
+    const int rc = guarded((rp_handle*)nullptr, [&] {
+        if (!name || mfcc_size < 1 || n_templates < 0 || (n_templates > 0 && (!names || !frames || !data)))
+            throw Error(RP_ERR_INVALID, "bad argument");
+        if (n_templates == 0) throw Error(RP_ERR_INVALID, "Can not create an empty wakeword");  // wakeword_ref.rs:52-54
+        WakewordRefData w;
+        w.name = name;
+        if (has_threshold) w.threshold = threshold;
+        if (has_avg_threshold) w.avg_threshold = avg_threshold;
+        w.rms_level = rms_level;
+        w.mfcc_size = mfcc_size;
+        for (int t = 0; t < n_templates; t++) {
+            if (!names[t] || !data[t] || frames[t] < 1) throw Error(RP_ERR_INVALID, "bad template");
+            FrameMatrix f;
+            f.rows = frames[t];
+            f.cols = mfcc_size;
+            f.v.assign(data[t], data[t] + (size_t)f.rows * f.cols);
+            w.samples_features.emplace_back(names[t], std::move(f));
+        }
+        w.avg_features = average_templates(w.samples_features);
+        const std::vector<uint8_t> bytes = encode_wakeword_ref(w);
+        written = (int64_t)bytes.size();
+        if (out) {
+            if (bytes.size() > out_cap) throw Error(RP_ERR_INVALID, "output buffer too small");
+            std::memcpy(out, bytes.data(), bytes.size());
+        }
+        return RP_OK;
+    });
+    return rc < 0 ? rc : written;
 }
 
 // ------------------------------------------------------------------ raw kernels

@@ -471,3 +471,66 @@ def test_batch_filters_match_oracle(kw):
             assert d["counter"] == w["counter"] and d["gain"] == w["gain"], (b, d, w)
             assert _rel(d["score"], w["score"]) < SCORE_RTOL and _rel(d["avg_score"], w["avg_score"]) < SCORE_RTOL
     assert bt.windows_scored() == total
+
+
+# ------------------------------------------------------------------ wakeword builder
+BUILD_CASES = [
+    ("oye_casa_g.rpw", [f"oye_casa_g_{i}.wav" for i in range(1, 6)]),
+    ("alexa.rpw", ["alexa.wav", "alexa2.wav", "alexa3.wav"]),
+]
+
+
+@pytest.mark.parametrize("rpw,wavs", BUILD_CASES)
+def test_builder_reproduces_reference_rpw(rpw, wavs, mfcc_variant):
+    """rp_wakeword_build (wav -> K1 -> CMN -> averager -> CBOR) over the wavs the reference's fixtures were built
+    from gives the reference's .rpw back: same names/shapes, rms_level exact, matrices within MFCC tolerance."""
+    fixture = O.Wakeword(open(golden(rpw), "rb").read())
+    samples = [(w, open(golden(w), "rb").read()) for w in wavs]
+    out = rp.build_wakeword(fixture.name, samples, 5)
+    built = O.Wakeword(out)                                   # the oracle's reader parses the product's file
+    info = rp.wakeword_inspect(out)                           # and so does the product's
+    assert info["name"] == fixture.name and info["mfcc_size"] == 5 and info["n_templates"] == len(wavs)
+    assert not info["has_threshold"] and not info["has_avg_threshold"]
+    assert float(built.rms_level) == float(fixture.rms_level)
+    got, want = dict(built.templates), dict(fixture.templates)
+    assert [n for n, _ in built.templates] == wavs            # insertion order kept
+    for k in want:
+        assert got[k].shape == want[k].shape and np.abs(got[k] - want[k]).max() < 2e-4, (k, np.abs(got[k] - want[k]).max())
+    assert built.avg_features.shape == fixture.avg_features.shape
+    assert np.abs(built.avg_features - fixture.avg_features).max() < 2e-4
+    # same result as the oracle's builder on the same inputs
+    ob = O.Wakeword(O.build_wakeword(fixture.name, samples, 5))
+    assert np.abs(built.avg_features - ob.avg_features).max() < 2e-4
+
+
+def test_built_wakeword_detects_like_the_reference_file():
+    """A wakeword built here from the fixture wavs, loaded into the detector, reproduces the goldens of
+    reference tests/detector.rs:25-38 (which use the reference-built file)."""
+    samples = [(f"oye_casa_g_{i}.wav", open(golden(f"oye_casa_g_{i}.wav"), "rb").read()) for i in range(1, 6)]
+    out = rp.build_wakeword("oye casa", samples, 5)
+    det = rp.Rustpotter(rp.default_config(sample_rate=16000, sample_format="i16", channels=1, score_mode="max", **BASE))
+    det.add_wakeword_from_buffer("wakeword", out)
+    _check(run_detection_simulation(det, two_wakeword_stream()),
+           [dict(avg_score=0.6495044, score=0.7310586), dict(avg_score=0.5804737, score=0.721843)])
+
+
+def test_builder_variants_and_errors():
+    wavs = [(w, open(golden(w), "rb").read()) for w in BUILD_CASES[1][1]]
+    for kw in (dict(from_files=False, threshold=0.4, avg_threshold=0.1), dict(mfcc_size=16), dict(mfcc_size=20)):
+        size = kw.pop("mfcc_size", 5)
+        got = O.Wakeword(rp.build_wakeword("a", wavs, size, **kw))
+        want = O.Wakeword(O.build_wakeword("a", wavs, size, **kw))
+        assert float(got.rms_level) == float(want.rms_level) and got.threshold == want.threshold
+        assert got.avg_threshold == want.avg_threshold and got.mfcc_size == size
+        for (gn, g), (wn, w) in zip(got.templates, want.templates):
+            assert gn == wn and g.shape == w.shape and np.abs(g - w).max() < 1e-3
+        assert np.abs(got.avg_features - want.avg_features).max() < 1e-3
+    single = O.Wakeword(rp.build_wakeword("a", wavs[:1], 5))
+    assert single.avg_features is None and len(single.templates) == 1
+    with pytest.raises(rp.RustpotterError):
+        rp.build_wakeword("a", [], 5)                                  # wakeword_ref.rs:52-54
+    with pytest.raises(rp.RustpotterError):
+        rp.build_wakeword("a", [("x", b"not a wav file at all")], 5)
+    with pytest.raises(rp.RustpotterError):                            # 30 ms of audio: no frame
+        hdr = wavs[0][1][:44]
+        rp.build_wakeword("a", [("x", hdr + bytes(480 * 2))], 5)

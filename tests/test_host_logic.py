@@ -157,6 +157,53 @@ def test_host_state_machine_matches_oracle_detector(rpw_name, kw):
         assert gd["scores"] == wd["scores"]
 
 
+@pytest.mark.parametrize("name", ["oye_casa_g.rpw", "alexa.rpw"])
+def test_averager_and_cbor_writer_reproduce_reference_file_bytes(name):
+    """rp_wakeword_from_features (MfccAverager::average, averager.rs:5-37, with the unbanded DTW path of
+    dtw.rs:11-55,106-138, + the ciborium layout of WakewordRef) fed the templates stored in a reference-built
+    .rpw must give back that file byte for byte: same averaged matrix bits, same field order, same float widths."""
+    buf = open(golden(name), "rb").read()
+    info = rp.wakeword_inspect(buf)
+    templates = [rp.wakeword_template(buf, t, info["mfcc_size"]) for t in range(info["n_templates"])]
+    out = rp.wakeword_from_features(info["name"], templates, info["rms_level"])
+    assert out == buf
+    # and the oracle reads the product-written file
+    ww = O.Wakeword(out)
+    assert ww.name == info["name"] and len(ww.templates) == info["n_templates"]
+
+
+def test_cbor_writer_options_and_float_widths():
+    """Option fields (threshold / avg_threshold / avg_features) and ciborium's smallest-lossless float width."""
+    rng = np.random.default_rng(5)
+    t0 = rng.standard_normal((7, 3)).astype(np.float32)
+    t0[0] = [0.0, 0.5, -2.0]                 # exact halves -> 3-byte floats
+    t0[1, 0] = np.float32(6.1035156e-05)     # smallest normal half
+    t0[1, 1] = np.float32(5.9604645e-08)     # smallest subnormal half
+    t0[1, 2] = np.float32(65504.0)           # largest half
+    t0[2, 0] = np.float32(65536.0)           # not a half
+    t0[2, 1] = np.float32(1e-30)
+    out = rp.wakeword_from_features("w", [("only", t0)], 0.25, threshold=0.5, avg_threshold=0.125)
+    info = rp.wakeword_inspect(out)
+    assert info["avg_frames"] == 0 and info["has_threshold"] and info["has_avg_threshold"]
+    assert info["threshold"] == 0.5 and info["avg_threshold"] == 0.125 and info["rms_level"] == 0.25
+    name, back = rp.wakeword_template(out, 0, 3)
+    assert name == "only" and np.array_equal(back, t0)
+    ww = O.Wakeword(out)                     # the oracle's reader agrees
+    assert np.array_equal(dict(ww.templates)["only"], t0) and ww.avg_features is None
+    # 7*3 floats: 6 of them fit a half (3 bytes instead of 5)
+    ref = O.encode_wakeword("w", [("only", t0)], None, 0.25, threshold=0.5, avg_threshold=0.125)
+    assert len(out) <= len(ref)
+    with pytest.raises(rp.RustpotterError):
+        rp.wakeword_from_features("w", [], 0.1)
+
+
+@pytest.mark.skipif(rp.device_count() > 0, reason="checks the no-GPU failure mode")
+def test_builder_fails_loudly_without_gpu():
+    wavs = [(w, open(golden(w), "rb").read()) for w in ("alexa.wav", "alexa2.wav")]
+    with pytest.raises(rp.RustpotterError):
+        rp.build_wakeword("alexa", wavs, 5)
+
+
 def test_judgement_modes_match_oracle_aggregate():
     """score_logic.h percentile/aggregate vs the oracle's (wakeword_comp.rs:38-49,108-139)."""
     rng = np.random.default_rng(5)

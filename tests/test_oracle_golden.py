@@ -102,6 +102,45 @@ def test_mfcc_matches_stored_templates(rpw, wavs):
         assert np.max(np.abs(m - t)) < 5e-5, (w, np.max(np.abs(m - t)))
 
 
+BUILD_CASES = [
+    ("oye_casa_g.rpw", [f"oye_casa_g_{i}.wav" for i in range(1, 6)]),
+    ("alexa.rpw", ["alexa.wav", "alexa2.wav", "alexa3.wav"]),
+]
+
+
+@pytest.mark.parametrize("rpw,wavs", BUILD_CASES)
+def test_builder_reproduces_reference_rpw(rpw, wavs):
+    """WakewordRef::new_from_sample_files (wakeword_ref_build.rs:47-91) over the fixture wavs: the oracle's
+    wav reader + extractor + CMN + MfccAverager + median rms must rebuild the reference's own .rpw."""
+    fixture = O.Wakeword(open(golden(rpw), "rb").read())
+    built = O.Wakeword(O.build_wakeword(fixture.name, [(w, open(golden(w), "rb").read()) for w in wavs], 5))
+    assert built.name == fixture.name and built.mfcc_size == 5
+    assert built.threshold is None and built.avg_threshold is None
+    assert float(built.rms_level) == float(fixture.rms_level)           # median of per-file median chunk rms: exact
+    got, want = dict(built.templates), dict(fixture.templates)
+    assert set(got) == set(want)
+    for k in want:
+        assert got[k].shape == want[k].shape and np.max(np.abs(got[k] - want[k])) < 5e-5, k
+    assert built.avg_features.shape == fixture.avg_features.shape
+    assert np.max(np.abs(built.avg_features - fixture.avg_features)) < 5e-5
+
+
+def test_builder_buffers_variant_and_errors():
+    """new_from_sample_buffers takes the MAX rms level (wakeword_ref_build.rs:28-30); one sample -> no average
+    (:97-99); no samples -> error (wakeword_ref.rs:52-54)."""
+    wavs = [(w, open(golden(w), "rb").read()) for w in BUILD_CASES[1][1]]
+    files = O.Wakeword(O.build_wakeword("a", wavs, 5, from_files=True))
+    bufs = O.Wakeword(O.build_wakeword("a", wavs, 5, threshold=0.4, avg_threshold=0.1, from_files=False))
+    assert float(bufs.rms_level) >= float(files.rms_level)
+    assert abs(bufs.threshold - 0.4) < 1e-7 and abs(bufs.avg_threshold - 0.1) < 1e-7
+    single = O.Wakeword(O.build_wakeword("a", wavs[:1], 5))
+    assert single.avg_features is None and len(single.templates) == 1
+    with pytest.raises(ValueError):
+        O.build_wakeword("a", [], 5)
+    wide = O.Wakeword(O.build_wakeword("a", wavs, 16))
+    assert wide.mfcc_size == 16 and wide.avg_features.shape[1] == 16
+
+
 def test_fixture_shapes():
     """SURVEY §4 fixture shapes."""
     ww = O.Wakeword(open(golden("oye_casa_g.rpw"), "rb").read())
