@@ -203,7 +203,7 @@ int rp_dtw_scores(const float* tmpl_dev, const int64_t* tmpl_off_dev, const int3
                   int64_t n_pairs, int d, int band, float score_ref, int cmn, float* out_dev, void* cuda_stream);
 /* Selects the DTW kernel variants (0 = automatic, 1 = generic reference-order kernels, 2 = tuned kernels,
  * 3 = tuned with the one-row-per-step streaming kernel, 4 = tuned with the two-windows-per-thread pipeline
- * kernel). For A/B measurements and parity tests. */
+ * kernel, 5 = tuned with the round-1 two-rows-per-step streaming kernel). For A/B measurements and parity tests. */
 int rp_set_dtw_variant(int variant);
 /* Selects the MFCC kernel: 0 = automatic (two-frames-per-warp TMA-staged kernel where it applies), 1 = one frame
  * per warp. For A/B measurements and parity tests. */

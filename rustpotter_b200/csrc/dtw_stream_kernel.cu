@@ -466,8 +466,13 @@ __global__ void __launch_bounds__(32) dtw_pairs_stream2_kernel(DtwPairsArgs a, i
 
 }  // namespace
 
-int g_stream_rows = 0;  // 0 = automatic, 1 = force the one-row-per-step kernel (A/B measurements)
+// 0 = automatic (v3 half-step kernel where it applies), 1 = one-row-per-step kernel, 2 = round-1 two-rows-per-step
+// kernel (both kept for A/B measurements and for windows 21..23)
+int g_stream_rows = 0;
 void set_dtw_stream_rows(int rows) { g_stream_rows = rows; }
+
+bool dtw_pairs_stream3_supported(const DtwPairsArgs& a);
+cudaError_t launch_dtw_pairs_stream3(const DtwPairsArgs& a, cudaStream_t stream);
 
 bool dtw_pairs_stream_supported(const DtwPairsArgs& a) {
     if (a.d != kD || a.cmn || a.tmpl_len || a.win_len) return false;
@@ -483,6 +488,7 @@ bool dtw_pairs_stream_supported(const DtwPairsArgs& a) {
 
 cudaError_t launch_dtw_pairs_stream(const DtwPairsArgs& a, cudaStream_t stream) {
     if (a.n_pairs <= 0) return cudaSuccess;
+    if (g_stream_rows == 0 && dtw_pairs_stream3_supported(a)) return launch_dtw_pairs_stream3(a, stream);
     const int m = a.tmpl_len_max, n = a.win_len_max;
     const int diff = m > n ? m - n : n - m;
     const int window = a.band > diff ? a.band : diff;

@@ -102,6 +102,9 @@ def _rel(a, b):
     # shapes that take the streaming kernel (d = 16, no CMN, window <= 23)
     (100, 100, 16, 5, False), (100, 100, 16, 20, False), (64, 72, 16, 9, False), (119, 97, 16, 5, False), (16, 8, 16, 5, False),
     (2, 2, 16, 5, False), (60, 7, 16, 60, False), (128, 105, 16, 23, False), (200, 192, 16, 11, False), (45, 50, 16, 2, False),
+    # half-step streaming kernel (window <= 20): odd/even last row, one-block and many-block windows, band 1
+    (120, 100, 16, 5, False), (121, 101, 16, 5, False), (100, 120, 16, 5, False), (9, 8, 16, 1, False), (41, 40, 16, 3, False),
+    (300, 290, 16, 12, False), (7, 3, 16, 4, False), (33, 17, 16, 16, False), (96, 97, 16, 20, False),
 ])
 def test_dtw_kernel_matches_oracle(m, n, d, band, cmn):
     torch = _torch()
@@ -121,8 +124,9 @@ def test_dtw_kernel_matches_oracle(m, n, d, band, cmn):
         ref.append(O.compare(a[p], wb, band, 0.22))
     # variant 1 = generic kernel (reference operation order, held to 5e-6); 0 = automatic choice
     # (streaming kernel where it applies; FFMA2 dots + rsqrt change the rounding, held to 3e-5)
-    # 3 = the one-row-per-step streaming kernel (0 prefers the two-rows-per-step one)
-    for variant, tol in ((1, 5e-6), (0, 3e-5), (3, 3e-5)):
+    # 3 = the one-row-per-step streaming kernel, 5 = the round-1 two-rows-per-step one (0 prefers the
+    # half-step kernel for windows <= 20)
+    for variant, tol in ((1, 5e-6), (0, 3e-5), (3, 3e-5), (5, 3e-5)):
         rp.set_dtw_variant(variant)
         got = rp.dtw_scores(torch.from_numpy(a).cuda(), torch.from_numpy(w).cuda(), band=band, cmn=cmn).cpu().numpy()
         rp.set_dtw_variant(0)
@@ -144,7 +148,7 @@ def test_dtw_stream_kernel_many_pairs_vs_generic():
     w = torch.randn((P, 100, 16), device="cuda", generator=g) * scale
     rp.set_dtw_variant(1)
     ref = rp.dtw_scores(a, w, band=5)
-    for variant in (0, 3):
+    for variant in (0, 3, 5):
         rp.set_dtw_variant(variant)
         got = rp.dtw_scores(a, w, band=5)
         rp.set_dtw_variant(0)
