@@ -124,9 +124,9 @@ def test_dtw_kernel_matches_oracle(m, n, d, band, cmn):
         ref.append(O.compare(a[p], wb, band, 0.22))
     # variant 1 = generic kernel (reference operation order, held to 5e-6); 0 = automatic choice
     # (streaming kernel where it applies; FFMA2 dots + rsqrt change the rounding, held to 3e-5)
-    # 3 = the one-row-per-step streaming kernel, 5 = the round-1 two-rows-per-step one (0 prefers the
-    # half-step kernel for windows <= 20)
-    for variant, tol in ((1, 5e-6), (0, 3e-5), (3, 3e-5), (5, 3e-5)):
+    # 3 = the one-row-per-step streaming kernel, 5 = the round-1 two-rows-per-step one, 6 = the v3 half-step
+    # kernel (0 prefers the v4 warp-per-block kernel for windows 3..20, then v3 for windows <= 20)
+    for variant, tol in ((1, 5e-6), (0, 3e-5), (3, 3e-5), (5, 3e-5), (6, 3e-5)):
         rp.set_dtw_variant(variant)
         got = rp.dtw_scores(torch.from_numpy(a).cuda(), torch.from_numpy(w).cuda(), band=band, cmn=cmn).cpu().numpy()
         rp.set_dtw_variant(0)
@@ -148,13 +148,41 @@ def test_dtw_stream_kernel_many_pairs_vs_generic():
     w = torch.randn((P, 100, 16), device="cuda", generator=g) * scale
     rp.set_dtw_variant(1)
     ref = rp.dtw_scores(a, w, band=5)
-    for variant in (0, 3, 5):
+    for variant in (0, 3, 5, 6):
         rp.set_dtw_variant(variant)
         got = rp.dtw_scores(a, w, band=5)
         rp.set_dtw_variant(0)
         rel = ((got - ref).abs() / ref.abs().clamp_min(1e-12)).max().item()
         assert rel < 3e-5, (variant, rel)
     assert float(ref.min()) > 0
+
+
+@pytest.mark.parametrize("band", [3, 4, 5, 7, 8, 11, 12, 13, 16, 17, 19, 20])
+def test_dtw_stream4_shape_sweep_vs_generic(band):
+    """The v4 streaming kernel (variant 0 for windows 3..20) against the reference-order generic kernel over
+    template/window lengths around every block and row-pair boundary: m odd/even, n on and off multiples
+    of 8, |m-n| below, at and above the band, one to many blocks, several groups with a partial last one."""
+    torch = _torch()
+    g = torch.Generator(device="cuda").manual_seed(1000 + band)
+    scale = torch.tensor([8, 4, 3, 2, 2, 1.5] + [1.0] * 10, device="cuda")
+    P = 75
+    shapes = [(2, 1), (3, 2), (5, 9), (8, 8), (9, 8), (16, 17), (17, 16), (24, 25), (31, 33), (40, 40), (41, 47), (64, 57),
+              (65, 64), (72, 80), (97, 104), (100, 100), (101, 100), (120, 100), (121, 101), (100, 120), (133, 129), (160, 168)]
+    for m, n in shapes:
+        if not 3 <= max(band, abs(m - n)) <= 20:
+            continue
+        a = torch.randn((P, m, 16), device="cuda", generator=g) * scale
+        w = torch.randn((P, n, 16), device="cuda", generator=g) * scale
+        a[3, m // 2] = 0.0
+        w[4, n // 2] = 0.0
+        rp.set_dtw_variant(1)
+        ref = rp.dtw_scores(a, w, band=band)
+        rp.set_dtw_variant(0)
+        got = rp.dtw_scores(a, w, band=band)
+        zero = ref == 0
+        assert bool((got[zero] == 0).all()), (m, n, band)
+        rel = ((got - ref).abs() / ref.abs().clamp_min(1e-12))[~zero]
+        assert rel.numel() == 0 or rel.max().item() < 3e-5, (m, n, band, rel.max().item(), int(rel.argmax()))
 
 
 def test_dtw_ragged_pairs():
