@@ -223,6 +223,11 @@ typedef struct rp_wakeword_info {
     float threshold, avg_threshold, rms_level;
     int32_t is_v2;
 } rp_wakeword_info;
+/* Static producer schedule of the streaming DTW kernel (dtw_stream4_kernel.cu) for uniform template length m,
+ * window length n and band: out[batch * 4 + slot] = 0 (nothing), k (template row pair k = rows 2k-1, 2k) or
+ * 0x8000 | block << 2 | quarter (a quarter of a window block of 8 columns). Returns the number of batches, or 0
+ * when the kernel does not take the shape. Exposed so that the schedule's invariants are tested without a GPU. */
+int rp_debug_stream4_schedule(int m, int n, int band, uint16_t* out, size_t out_cap);
 /* Parses a .rpw buffer (WakewordV2 then WakewordRef, detector.rs:152-163). */
 int rp_wakeword_inspect(const uint8_t* buf, size_t len, rp_wakeword_info* info);
 /* Copies template t (t == -1: avg_features) of a .rpw buffer: name (RP_NAME_MAX bytes) and

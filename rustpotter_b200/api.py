@@ -85,7 +85,7 @@ EXPORTED = [
     "rp_batch_set_cuda_stream", "rp_batch_process", "rp_batch_update_config", "rp_batch_reset",
     "rp_batch_windows_scored", "rp_batch_n_streams", "rp_batch_max_mfcc_frames", "rp_batch_last_timings",
     "rp_batch_last_launches", "rp_batch_copy_last_scores", "rp_mfcc_frames", "rp_dtw_scores", "rp_set_dtw_variant", "rp_set_mfcc_variant", "rp_wakeword_inspect",
-    "rp_wakeword_template", "rp_host_replay", "rp_wakeword_build", "rp_wakeword_from_features",
+    "rp_wakeword_template", "rp_host_replay", "rp_wakeword_build", "rp_wakeword_from_features", "rp_debug_stream4_schedule",
 ]
 
 
@@ -411,6 +411,16 @@ def build_wakeword(name: str, samples: list[tuple[str, bytes]], mfcc_size: int =
 
 
 # ---------------------------------------------------------------- host-logic hooks (no GPU)
+def stream4_schedule(m: int, n: int, band: int):
+    """Producer schedule of the streaming DTW kernel: uint16 [batches][4], or None if the kernel does not take the shape."""
+    L = lib()
+    L.rp_debug_stream4_schedule.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint16), C.c_size_t]
+    L.rp_debug_stream4_schedule.restype = C.c_int
+    out = np.zeros((128, 4), np.uint16)
+    nb = L.rp_debug_stream4_schedule(m, n, band, out.ctypes.data_as(C.POINTER(C.c_uint16)), out.size)
+    return out[:nb].copy() if nb > 0 else None
+
+
 def wakeword_inspect(buf: bytes) -> dict:
     info = WakewordInfo()
     _check(lib().rp_wakeword_inspect(buf, len(buf), C.byref(info)))

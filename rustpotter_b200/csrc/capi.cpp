@@ -517,6 +517,16 @@ int rp_set_mfcc_variant(int v) {
 }
 
 // ------------------------------------------------------------------ host-logic hooks
+int rp_debug_stream4_schedule(int m, int n, int band, uint16_t* out, size_t out_cap) {
+    Stream4Sched s;
+    int n_super = 0;
+    if (!build_stream4_schedule(m, n, band, &s, &n_super)) return 0;
+    for (int c = 0; c < n_super; c++)
+        for (int k = 0; k < 4; k++)
+            if (out && (size_t)(c * 4 + k) < out_cap) out[c * 4 + k] = s.unit[c][k];
+    return n_super;
+}
+
 int rp_wakeword_inspect(const uint8_t* buf, size_t len, rp_wakeword_info* info) {
     if (!buf || !info) return RP_ERR_INVALID;
     return guarded((rp_handle*)nullptr, [&] {

@@ -59,6 +59,12 @@ cudaError_t launch_dtw_pairs_generic(const DtwPairsArgs& a, cudaStream_t stream)
 bool dtw_pairs_stream_supported(const DtwPairsArgs& a);
 cudaError_t launch_dtw_pairs_stream(const DtwPairsArgs& a, cudaStream_t stream);
 void set_dtw_stream_rows(int rows);
+// K2s v4 (dtw_stream4_kernel.cu): what its producer warps fetch in which batch; built on the host per (m, n, band).
+constexpr int STREAM4_MAX_BATCHES = 120;
+struct Stream4Sched {
+    unsigned short unit[STREAM4_MAX_BATCHES][4];
+};
+bool build_stream4_schedule(int m, int n, int band, Stream4Sched* out, int* n_super_out);
 
 // Pipeline scoring: every new frame j of every stream closes a window; slot s scores the first
 // slot_len[s] frames of that window (after CMN) against template s.

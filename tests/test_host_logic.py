@@ -249,3 +249,71 @@ def test_mfcc_tables_build_for_every_mfcc_size(tmp_path):
                    check=True, timeout=120)
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout
+
+
+# ------------------------------------------------------------------ K2s v4 producer schedule (host-built, no GPU)
+def _stream4_consumer_reads(m, n, band):
+    """Re-derives, from the kernel's documented geometry only, which ring slots and staged blocks the consumer
+    warps read in which super-step (dtw_stream4_kernel.cu: block B handles row pair u = st - 2B at step st while
+    4B + 1 - w/2 <= u <= 4B + 4 + (w+1)/2; it reads row pair u, looks one row pair ahead, and switches to
+    block B+4 after its last step)."""
+    w = max(band, abs(m - n))
+    nb = (n + 7) // 8
+    half = m // 2
+    steps = half + 2 * (nb - 1)
+    fin0 = 4 + (w + 1) // 2
+    rows, blocks = {}, {}          # row pair -> (first super-step read, last), block -> super-step of the switch read
+    for B in range(nb):
+        ufirst, ulast = max(1, 4 * B + 1 - w // 2), 4 * B + fin0
+        for st in range(1, steps + 1):
+            u = st - 2 * B
+            if ufirst <= u <= ulast:
+                S = (st + 1) // 2
+                for k in (u, u + 1) if u + 1 <= ulast else (u,):
+                    lo, hi = rows.get(k, (S, S))
+                    rows[k] = (min(lo, S), max(hi, S))
+                if u == ulast and st < steps and B + 4 < nb:
+                    blocks[B + 4] = S
+    return w, nb, steps, rows, blocks
+
+
+def test_stream4_schedule_invariants():
+    from rustpotter_b200 import api
+    checked = 0
+    for m in list(range(2, 40)) + [57, 64, 99, 100, 101, 119, 120, 121, 150, 168, 200]:
+        for n in sorted({max(1, m + d) for d in (-20, -19, -13, -8, -7, -3, -1, 0, 1, 2, 5, 8, 12, 17, 20)}):
+            for band in (3, 5, 8, 12, 16, 17, 20):
+                sched = api.stream4_schedule(m, n, band)
+                w = max(band, abs(m - n))
+                if sched is None:
+                    assert not (3 <= w <= 20 and m // 2 + 2 * ((n + 7) // 8 - 1) <= 236), (m, n, band)
+                    continue
+                w, nb, steps, rows, blocks = _stream4_consumer_reads(m, n, band)
+                assert len(sched) == (steps + 1) // 2
+                row_batch, quarter_batch = {}, {}
+                for c, units in enumerate(sched):
+                    for code in units:
+                        code = int(code)
+                        if code == 0:
+                            continue
+                        if code & 0x8000:
+                            quarter_batch[((code & 0x7fff) >> 2, code & 3)] = c
+                        else:
+                            assert code not in row_batch
+                            row_batch[code] = c
+                kmax = (m + 1) // 2
+                for k, (first, last) in rows.items():
+                    if k > kmax:
+                        continue            # beyond the template: only rows > m-1 of non-final blocks touch these slots
+                    # stored (batch c is visible from super-step c+1) before the first read ...
+                    assert k in row_batch and row_batch[k] + 1 <= first, (m, n, band, k, row_batch.get(k), first)
+                    # ... and not overwritten (slot k % 16) until after the last one: batch c stores during super-step c
+                    if k + 16 in row_batch:
+                        assert row_batch[k + 16] > last, (m, n, band, k, row_batch[k + 16], last)
+                for B, S in blocks.items():
+                    for j in range(4):
+                        assert quarter_batch.get((B, j), 1 << 30) + 1 <= S, (m, n, band, B, j, S)
+                        if B + 2 in blocks or (B + 2, j) in quarter_batch:
+                            assert quarter_batch.get((B + 2, j), 1 << 30) > S, (m, n, band, B, j)
+                checked += 1
+    assert checked > 1500
