@@ -17,12 +17,12 @@
 //    Block b runs two steps behind block b-1, so one warp owns blocks b, b+4, b+8, .. back to back, boundary
 //    columns travel through a 4-deep exchange array in shared memory, and the consumers meet only every
 //    SECOND step ("super-step").
-//  * PRODUCER warps 4..7 (setmaxnreg hands their registers to the consumers: 32 vs 224): HBM -> registers ->
+//  * PRODUCER warps 4..7 (setmaxnreg hands their registers to the consumers: 56 vs 200): HBM -> registers ->
 //    unit length -> shared memory. Per super-step they fetch the template row pairs and the quarters of the
 //    next window block that a host-built static schedule (Stream4Sched, checked on the CPU by
 //    tests/test_host_logic.py) assigns to it, 32 bytes per thread, four threads per 128 contiguous bytes of
 //    one pair. No cp.async raw copy and no in-ring rewrite: shared-memory traffic is 53 KB per pair (v3: 81).
-//    Producers run one super-step ahead of the consumers: two "full" and two "empty" named barriers
+//    Producers run up to two super-steps ahead of the consumers: four "full" and four "empty" named barriers
 //    (bar.arrive / bar.sync, 256 threads) order the ring slots, so a late HBM line stalls nobody.
 //  * A block switch is 32 conflict-free LDS.128 (the staged block is already negated and normalised).
 //
@@ -30,6 +30,7 @@
 // Everything else takes the older kernels.
 #include <cfloat>
 #include <cmath>
+#include <algorithm>
 #include <cstring>
 
 #include "kernels.h"
@@ -56,8 +57,9 @@ constexpr int XDRAIN_F = NW * 32;                     // one more value per warp
 constexpr int SMEM_FLOATS = RING_F + STAGE_F + XCH_F + XDRAIN_F;
 constexpr int SMEM_BYTES = SMEM_FLOATS * 4;           // 103,936 bytes: two CTAs per SM
 constexpr int MIN_WINDOW = 3, MAX_WINDOW = 20;
-constexpr int CONSUMER_REGS = 224, PRODUCER_REGS = 32;
-constexpr int BAR_FULL = 1, BAR_EMPTY = 3;            // named barriers 1,2 (full) and 3,4 (empty)
+constexpr int CONSUMER_REGS = 200, PRODUCER_REGS = 56;
+constexpr int DEPTH = 2;                              // super-steps the producers may run ahead of the consumers
+constexpr int BAR_FULL = 1, BAR_EMPTY = 5, BAR_CONSUMERS = 9, BAR_GROUP = 10;   // named barriers 1..4 (full), 5..8 (empty)
 
 typedef unsigned long long f2;
 
@@ -185,29 +187,26 @@ __device__ __forceinline__ void half_step(const f2 (&ar)[8], const f2 (&bcol)[CB
     }
 }
 
-// Band mask of a step: bit i <-> d = r - c = (2u-1) - c0 + (i - 7), valid iff -w+1 <= d <= w. Bits 7-j (row 2u-1) and
-// 8-j (row 2u) are the cells of column c0+j, bits 8 and 9 the two cells of column c0-1 (the left neighbour's last).
-__device__ __forceinline__ unsigned band_mask(int u, int c0, int w) {
-    const int t = 2 * u - c0 + w - 2;
-    const int lo = min(max(7 - t, 0), 10), hi = min(max(7 - t + 2 * w, 0), 10);
-    return (1u << hi) - (1u << lo);
-}
+// Band mask of a step (built on the host, bits 12..21 of the control word): bit i <-> d = r - c = (2u-1) - c0 + (i - 7),
+// valid iff -w+1 <= d <= w. Bits 7-j (row 2u-1) and 8-j (row 2u) are the cells of column c0+j, bits 8 and 9 the two cells
+// of column c0-1 (the left neighbour's last).
 
-// One step of a block: template rows 2u-1 and 2u against the eight columns. FULL: every cell is inside the band.
+// One step of a block: template rows 2u-1 and 2u (rp0 = ring slot of row pair u, rp1 = of u+1) against the eight columns.
+// FULL: every cell is inside the band.
 template <bool FULL>
-__device__ __forceinline__ void block_step(const float* __restrict__ ring_p, int u, unsigned M, float li1, float li2p, float li1_prev,
+__device__ __forceinline__ void block_step(const float* __restrict__ rp0, const float* __restrict__ rp1, unsigned M, float li1, float li2p, float li1_prev,
                                            const f2 (&bcol)[CB][8], f2 (&ar1)[8], float (&D1)[CB], float (&D2)[CB], float (&cost2)[CB],
                                            float& out1, float& out2, f2 one) {
     f2 ar2[8], acc[CB];
     float cost1[CB];
     // ---- H1: dots of row 2u-1, DP of row 2u-2
-    load_row(ring_p + (u & (SLOTS - 1)) * SLOT_F + kD, ar2);
+    load_row(rp0 + kD, ar2);
     half_step(ar1, bcol, acc, cost2, D1, D2, li2p, li1_prev, one);
     out2 = D2[CB - 1];
 #pragma unroll
     for (int j = 0; j < CB; j++) cost1[j] = (FULL || ((M >> (7 - j)) & 1u)) ? hsum(acc[j]) : INFINITY;
     // ---- H2: dots of row 2u, DP of row 2u-1
-    load_row(ring_p + ((u + 1) & (SLOTS - 1)) * SLOT_F, ar1);
+    load_row(rp1, ar1);
     half_step(ar2, bcol, acc, cost1, D2, D1, li1, li2p, one);
     out1 = D1[CB - 1];
 #pragma unroll
@@ -234,21 +233,45 @@ __device__ __forceinline__ Geometry make_geometry(const DtwPairsArgs& a, int win
 }
 
 // ------------------------------------------------------------------------------------------------ consumers
-__device__ __forceinline__ void consumer_loop(const DtwPairsArgs& a, int64_t n_groups, const Geometry& g, float* smem) {
+// Control word of one (warp, step), built on the host (build_stream4_schedule): the consumers' step prologue is one
+// uniform load and a few bit tests instead of a serial chain of index arithmetic.
+constexpr unsigned CTL_ACTIVE = 1u << 0;        // the warp's block is inside the band at this step
+constexpr unsigned CTL_FRESH = 1u << 1;         // first step of a block: no look-ahead row was loaded
+constexpr unsigned CTL_FULL = 1u << 2;          // all 16 cells inside the band: no masks
+constexpr unsigned CTL_SWITCH = 1u << 3;        // last step of the block (and not the last step of the group)
+constexpr unsigned CTL_OK1 = 1u << 4;           // cell (2u-1, c0-1) is inside the band and a left block exists
+constexpr unsigned CTL_OK2 = 1u << 5;           // cell (2u,   c0-1) ...
+constexpr unsigned CTL_OK2PREV = 1u << 6;       // (fresh steps) cell (2u-2, c0-1) ...
+constexpr unsigned CTL_DRAIN_RD = 1u << 7;      // D[2u-2][c0-1] comes from the left warp's drain slot
+constexpr unsigned CTL_HAS_LEFT = 1u << 8;      // block > 0
+constexpr unsigned CTL_NEXT_EXISTS = 1u << 9;   // (switch steps) block + 4 exists
+constexpr unsigned CTL_NEXT_PARITY = 1u << 10;  // (switch steps) its staging slot
+constexpr unsigned CTL_NEXT_LAST = 1u << 11;    // (switch steps) it is the pair's last block
+constexpr int CTL_MASK_SHIFT = 12;              // 10 bits: band mask
+constexpr int CTL_SLOT_SHIFT = 22;              // 4 bits: row pair u & 15
+
+__device__ __forceinline__ void consumer_loop(const DtwPairsArgs& a, int64_t n_groups, const Geometry& g, float* smem, const Stream4Sched& sched) {
     const int lane = threadIdx.x & 31;
     const int wid = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform, 0..3
-    const int m = g.m, n = g.n, w = g.w, n_blocks = g.n_blocks, fin0 = g.fin0, steps = g.steps;
+    const int m = g.m, n = g.n, n_blocks = g.n_blocks, steps = g.steps;
     const int owner_w = (n_blocks - 1) & (NW - 1);
     const int left_w = (wid + NW - 1) & (NW - 1);
     const f2 one = pk(1.f, 0.f);
-    const float* const ring_p = smem + lane * RING_PAIR_F;
-    const float* const stage_p = smem + RING_F + lane * STAGE_PAIR_F;
-    float* const xch_all = smem + RING_F + STAGE_F;
-    float* const xch_w = xch_all + wid * (XS * 2 * 32) + lane;
-    const float* const xch_r = xch_all + left_w * (XS * 2 * 32) + lane;
-    float* const xdrain_w = xch_all + XCH_F + wid * 32 + lane;
-    const float* const xdrain_r = xch_all + XCH_F + left_w * 32 + lane;
-    unsigned gc = 0;   // super-steps done by this CTA's consumers (prologues included)
+    // shared-memory byte offsets, kept opaque so that they stay in registers instead of being recomputed from the thread id
+    unsigned ring_o = (unsigned)(lane * RING_PAIR_F * 4);
+    unsigned stage_o = (unsigned)((RING_F + lane * STAGE_PAIR_F) * 4);
+    unsigned xw_o = (unsigned)((RING_F + STAGE_F + wid * (XS * 2 * 32) + lane) * 4);
+    unsigned xr_o = (unsigned)((RING_F + STAGE_F + left_w * (XS * 2 * 32) + lane) * 4);
+    unsigned dw_o = (unsigned)((RING_F + STAGE_F + XCH_F + wid * 32 + lane) * 4);
+    unsigned dr_o = (unsigned)((RING_F + STAGE_F + XCH_F + left_w * 32 + lane) * 4);
+    asm volatile("" : "+r"(ring_o), "+r"(stage_o), "+r"(xw_o), "+r"(xr_o), "+r"(dw_o), "+r"(dr_o));
+    char* const sm = reinterpret_cast<char*>(smem);
+    const float* const ring_p = reinterpret_cast<const float*>(sm + ring_o);
+    const float* const stage_p = reinterpret_cast<const float*>(sm + stage_o);
+    float* const xch_w = reinterpret_cast<float*>(sm + xw_o);
+    const float* const xch_r = reinterpret_cast<const float*>(sm + xr_o);
+    float* const xdrain_w = reinterpret_cast<float*>(sm + dw_o);
+    const float* const xdrain_r = reinterpret_cast<const float*>(sm + dr_o);
 
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         const int64_t p = grp * PPG + lane;
@@ -257,10 +280,10 @@ __device__ __forceinline__ void consumer_loop(const DtwPairsArgs& a, int64_t n_g
         const float* const win = a.win + (a.win_off ? a.win_off[pc] : pc * (int64_t)n * kD);
 
         // ---- super-step 0: the warp's first block straight from global memory (the producers fill the ring meanwhile)
-        int B = wid;
+        bool on_last = wid == n_blocks - 1;
         f2 bcol[CB][8];
-        if (B < n_blocks) {
-            load_block_global(win, n, B, bcol);
+        if (wid < n_blocks) {
+            load_block_global(win, n, wid, bcol);
         } else {
 #pragma unroll
             for (int j = 0; j < CB; j++)
@@ -281,85 +304,88 @@ __device__ __forceinline__ void consumer_loop(const DtwPairsArgs& a, int64_t n_g
         f2 ar1[8];
 #pragma unroll
         for (int q = 0; q < 8; q++) ar1[q] = 0ull;
-        if (gc > 0) bar_sync(BAR_FULL + ((gc - 1) & 1));   // (keeps the barrier phases of the two roles in step)
-        bar_arrive(BAR_EMPTY + (gc & 1));
-        gc++;
+        if (0 <= g.n_super - 1 - DEPTH) bar_arrive(BAR_EMPTY);   // super-step 0 is over (nothing was read)
 
+        unsigned ctl_next = sched.ctl[wid][1];
         for (int S = 1; S <= g.n_super; S++) {
-            bar_sync(BAR_FULL + ((gc - 1) & 1));   // what the producers stored for this super-step, and the neighbours' boundary values
+            bar_sync(BAR_FULL + ((S - 1) & 3));   // batch S-1 of the producers, and the neighbours' boundary values
 #pragma unroll 1
             for (int st = 2 * S - 1; st <= min(2 * S, steps); st++) {
-                const int u = st - SIGMA * B;
-                const int ufirst = max(1, 4 * B + 1 - (w >> 1));
-                const int ulast = 4 * B + fin0;
-                if (B < n_blocks && u >= ufirst && u <= ulast) {
-                    const int c0 = B * CB + 1;
-                    if (u == ufirst) {   // fresh block: no look-ahead happened, and the step before it was skipped
-                        load_row(ring_p + (u & (SLOTS - 1)) * SLOT_F, ar1);
-                        ok2_prev = ((band_mask(u - 1, c0, w) >> 9) & 1u) && B > 0;
-                    }
-                    const unsigned M = band_mask(u, c0, w);
-                    const bool ok1 = ((M >> 8) & 1u) && B > 0;
-                    const bool ok2 = ((M >> 9) & 1u) && B > 0;
-                    float shf1 = INFINITY, shf2 = INFINITY;
-                    if (B > 0) {
-                        // D[2u-2][c0-1]: the left block's H1 of row pair u, or its drain if row pair u-1 was its last
-                        shf2 = (u == 4 * (B - 1) + fin0 + 1) ? xdrain_r[0] : xch_r[(u & (XS - 1)) * 64];
-                        shf1 = xch_r[(u & (XS - 1)) * 64 + 32];
-                    }
-                    const float li2p = ok2_prev ? shf2 : dseed;   // left input of row 2u-2 = diagonal input of row 2u-1
-                    const float li1 = ok1 ? shf1 : INFINITY;      // left input of row 2u-1 = diagonal input of row 2u
-                    dseed = INFINITY;
-                    if ((M & 0x1ffu) == 0x1ffu)
-                        block_step<true>(ring_p, u, M, li1, li2p, li1_prev, bcol, ar1, D1, D2, cost2, out1, out2, one);
-                    else
-                        block_step<false>(ring_p, u, M, li1, li2p, li1_prev, bcol, ar1, D1, D2, cost2, out1, out2, one);
-                    li1_prev = li1;
-                    ok2_prev = ok2;
-                    xch_w[(u & (XS - 1)) * 64] = out2;
-                    xch_w[(u & (XS - 1)) * 64 + 32] = out1;
-                    if (u == ulast && st < steps) {   // block finished
-                        {   // DP of its last row (2*ulast): nothing to its left is in the band any more; the right neighbour reads D2[7]
-                            float left = INFINITY, diag = li1_prev;
-#pragma unroll
-                            for (int j = 0; j < CB; j++) {
-                                const float up = D1[j];
-                                const float v = cost2[j] + min3(up, diag, left);
-                                diag = up;
-                                left = v;
-                            }
-                            xdrain_w[0] = left;
-                        }
-                        // the warp's next block, already staged (negated, unit length)
-                        B += NW;
-                        if (B < n_blocks) load_block_staged(stage_p + (B & 1) * (CB * kD), bcol);
+                const unsigned ctl = ctl_next;
+                ctl_next = sched.ctl[wid][st + 1];   // (the table has one spare entry)
+                if (!(ctl & CTL_ACTIVE)) continue;
+                const unsigned so = ((ctl >> CTL_SLOT_SHIFT) & 15u) * (SLOT_F * 4);   // byte offset of row pair u in the ring
+                const unsigned so1 = (so + SLOT_F * 4) & (SLOTS * SLOT_F * 4 - 1);      // ... of row pair u+1
+                const unsigned xo = ((ctl >> CTL_SLOT_SHIFT) & 3u) * 256;               // ... of row pair u in the exchange array
+                if (ctl & CTL_FRESH) {   // fresh block: no look-ahead happened, and the step before it was skipped
+                    load_row(reinterpret_cast<const float*>(reinterpret_cast<const char*>(ring_p) + so), ar1);
+                    ok2_prev = (ctl & CTL_OK2PREV) != 0;
+                }
+                float shf1 = INFINITY, shf2 = INFINITY;
+                if (ctl & CTL_HAS_LEFT) {
+                    // D[2u-2][c0-1]: the left block's H1 of row pair u, or its drain if row pair u-1 was its last
+                    const float* x = reinterpret_cast<const float*>(reinterpret_cast<const char*>(xch_r) + xo);
+                    shf2 = (ctl & CTL_DRAIN_RD) ? xdrain_r[0] : x[0];
+                    shf1 = x[32];
+                }
+                const float li2p = ok2_prev ? shf2 : dseed;              // left input of row 2u-2 = diagonal input of row 2u-1
+                const float li1 = (ctl & CTL_OK1) ? shf1 : INFINITY;     // left input of row 2u-1 = diagonal input of row 2u
+                dseed = INFINITY;
+                const float* const rp0 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(ring_p) + so);
+                const float* const rp1 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(ring_p) + so1);
+                if (ctl & CTL_FULL)
+                    block_step<true>(rp0, rp1, 0u, li1, li2p, li1_prev, bcol, ar1, D1, D2, cost2, out1, out2, one);
+                else
+                    block_step<false>(rp0, rp1, (ctl >> CTL_MASK_SHIFT) & 0x3ffu, li1, li2p, li1_prev, bcol, ar1, D1, D2, cost2, out1, out2, one);
+                li1_prev = li1;
+                ok2_prev = (ctl & CTL_OK2) != 0;
+                {
+                    float* x = reinterpret_cast<float*>(reinterpret_cast<char*>(xch_w) + xo);
+                    x[0] = out2;
+                    x[32] = out1;
+                }
+                if (ctl & CTL_SWITCH) {   // block finished
+                    {   // DP of its last row (2*ulast): nothing to its left is in the band any more; the right neighbour reads D2[7]
+                        float left = INFINITY, diag = li1_prev;
 #pragma unroll
                         for (int j = 0; j < CB; j++) {
-                            D1[j] = INFINITY;
-                            D2[j] = INFINITY;
-                            cost2[j] = INFINITY;
+                            const float up = D1[j];
+                            const float v = cost2[j] + min3(up, diag, left);
+                            diag = up;
+                            left = v;
                         }
-                        li1_prev = INFINITY;
-                        ok2_prev = false;
+                        xdrain_w[0] = left;
                     }
+                    // the warp's next block, already staged (negated, unit length)
+                    if (ctl & CTL_NEXT_EXISTS) load_block_staged(stage_p + ((ctl & CTL_NEXT_PARITY) ? CB * kD : 0), bcol);
+                    on_last = (ctl & CTL_NEXT_LAST) != 0;
+#pragma unroll
+                    for (int j = 0; j < CB; j++) {
+                        D1[j] = INFINITY;
+                        D2[j] = INFINITY;
+                        cost2[j] = INFINITY;
+                    }
+                    li1_prev = INFINITY;
+                    ok2_prev = false;
                 }
             }
-            // this super-step's ring and stage reads are over (nobody waits for the CTA's very last one)
-            if (S < g.n_super || grp + gridDim.x < n_groups) bar_arrive(BAR_EMPTY + (gc & 1));
-            gc++;
+            // this super-step's ring and stage reads are over (batch S+DEPTH waits for it, if there is one)
+            if (S <= g.n_super - 1 - DEPTH) bar_arrive(BAR_EMPTY + (S & 3));
         }
 
         // ---- result: the warp that owns the last block
+        // the group's reads of the ring are over: the producers may store the next group's first batches
+        if (grp + gridDim.x < n_groups) bar_arrive(BAR_GROUP);
         // the drain of the last row needs the left neighbour's last values: one more consumer-only rendezvous
-        asm volatile("bar.sync %0, %1;" ::"n"(5), "n"(NW * 32) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"n"(BAR_CONSUMERS), "n"(NW * 32) : "memory");
         if (wid == owner_w) {
             const int Bl = n_blocks - 1;
             float res = INFINITY;
-            if (B == Bl) {
+            if (on_last) {   // still on the last block: the result cell is inside its band
                 if (!(g.last_row & 1)) {
-                    const int u = steps + 1 - SIGMA * Bl;
+                    // drain: DP of the last step's second row (row 2*half == m-1)
                     float left = dseed;
-                    if (ok2_prev) left = (u == 4 * (Bl - 1) + fin0 + 1) ? xdrain_r[0] : xch_r[(u & (XS - 1)) * 64];
+                    if (ok2_prev) left = sched.res_from_drain ? xdrain_r[0] : xch_r[sched.res_slot * 64];
                     float diag = li1_prev;
 #pragma unroll
                     for (int j = 0; j < CB; j++) {
@@ -392,7 +418,6 @@ __device__ __forceinline__ void producer_loop(const DtwPairsArgs& a, int64_t n_g
     const int m = g.m, n = g.n, n_blocks = g.n_blocks;
     float* const ring_f = smem + fp * RING_PAIR_F + part * 8;
     float* const stage_f = smem + RING_F + fp * STAGE_PAIR_F + my_row * kD + (part & 1) * 8;
-    unsigned gi = 0;   // batches done by this CTA's producers
 
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         const int64_t pf = min(grp * PPG + fp, a.n_pairs - 1);
@@ -412,57 +437,43 @@ __device__ __forceinline__ void producer_loop(const DtwPairsArgs& a, int64_t n_g
                 for (int b = 0; b < NW; b++) prefetch_l2(wn + (size_t)min(b * CB + 2 * part, n - 1) * kD);
             }
         }
-        for (int c = 0; c <= g.n_super; c++) {
-            // batch c: what the consumers first read in super-step c+1 (the last batch of a group is empty)
+        for (int c = 0; c < g.n_super; c++) {
+            // batch c: what the consumers first read in super-step c+1.
+            // All loads first (they need no shared memory), then the wait for the ring slots, then scale and store.
+            ulonglong2 v[4][2];
+            float* dst[4];
+            float sign[4];
 #pragma unroll
-            for (int sb = 0; sb < 2; sb++) {
-                const unsigned ua = sched.unit[c][2 * sb], ub = sched.unit[c][2 * sb + 1];
-                ulonglong2 va0 = make_ulonglong2(0ull, 0ull), va1 = va0, vb0 = va0, vb1 = va0;
-                float* da = ring_f;
-                float* db = ring_f;
-                float sa = 1.f, sb_sign = 1.f;
-                if (ua) {
-                    if (ua & 0x8000u) {
-                        const int Bq = (ua & 0x7fffu) >> 2, j = ua & 3u;
-                        const int col = min(Bq * CB + 2 * j + my_row, n - 1);
-                        ldg32(winf + (size_t)col * kD + (part & 1) * 8, va0, va1);
-                        if (part == 0 && Bq + 1 < n_blocks) prefetch_l2(winf + (size_t)min((Bq + 1) * CB + 2 * j, n - 1) * kD);
-                        da = stage_f + (Bq & 1) * (CB * kD) + 2 * j * kD;
-                        sa = -1.f;
-                    } else {
-                        const int k = (int)ua;
-                        const float* src = tmplf + (size_t)(2 * k - 2) * kD + part * 8;
-                        if (2 * k - 1 + my_row <= m) ldg32(src, va0, va1);
-                        if (part == 0 && 2 * (k + 8) - 1 <= m) prefetch_l2(src + 8 * SLOT_F);
-                        da = ring_f + (k & (SLOTS - 1)) * SLOT_F;
-                    }
-                }
-                if (ub) {
-                    if (ub & 0x8000u) {
-                        const int Bq = (ub & 0x7fffu) >> 2, j = ub & 3u;
-                        const int col = min(Bq * CB + 2 * j + my_row, n - 1);
-                        ldg32(winf + (size_t)col * kD + (part & 1) * 8, vb0, vb1);
-                        if (part == 0 && Bq + 1 < n_blocks) prefetch_l2(winf + (size_t)min((Bq + 1) * CB + 2 * j, n - 1) * kD);
-                        db = stage_f + (Bq & 1) * (CB * kD) + 2 * j * kD;
-                        sb_sign = -1.f;
-                    } else {
-                        const int k = (int)ub;
-                        const float* src = tmplf + (size_t)(2 * k - 2) * kD + part * 8;
-                        if (2 * k - 1 + my_row <= m) ldg32(src, vb0, vb1);
-                        if (part == 0 && 2 * (k + 8) - 1 <= m) prefetch_l2(src + 8 * SLOT_F);
-                        db = ring_f + (k & (SLOTS - 1)) * SLOT_F;
-                    }
-                }
-                // the slots this batch overwrites were last read in super-step c-1 at the latest (Stream4Sched invariant)
-                if (sb == 0 && gi > 0) bar_sync(BAR_EMPTY + ((gi - 1) & 1));
-                if (ua | ub) {   // uniform; the shuffle inside needs every lane
-                    norm_store(va0, va1, da, sa, ua != 0);
-                    norm_store(vb0, vb1, db, sb_sign, ub != 0);
+            for (int i = 0; i < 4; i++) {
+                const unsigned un = sched.unit[c][i];
+                v[i][0] = make_ulonglong2(0ull, 0ull);
+                v[i][1] = v[i][0];
+                dst[i] = nullptr;
+                sign[i] = 1.f;
+                if (un & 0x8000u) {
+                    const int Bq = (un & 0x7fffu) >> 2, j = un & 3u;
+                    const int col = min(Bq * CB + 2 * j + my_row, n - 1);
+                    ldg32(winf + (size_t)col * kD + (part & 1) * 8, v[i][0], v[i][1]);
+                    if (part == 0 && Bq + 1 < n_blocks) prefetch_l2(winf + (size_t)min((Bq + 1) * CB + 2 * j, n - 1) * kD);
+                    dst[i] = stage_f + (Bq & 1) * (CB * kD) + 2 * j * kD;
+                    sign[i] = -1.f;
+                } else if (un) {
+                    const int k = (int)un;
+                    const float* src = tmplf + (size_t)(2 * k - 2) * kD + part * 8;
+                    if (2 * k - 1 + my_row <= m) ldg32(src, v[i][0], v[i][1]);
+                    if (part == 0 && 2 * (k + 8) - 1 <= m) prefetch_l2(src + 8 * SLOT_F);
+                    dst[i] = ring_f + (k & (SLOTS - 1)) * SLOT_F;
                 }
             }
+            // the slots this batch overwrites were last read in super-step c-DEPTH at the latest (Stream4Sched invariant),
+            // or by the previous group
+            if (c >= DEPTH) bar_sync(BAR_EMPTY + ((c - DEPTH) & 3));
+            else if (c == 0 && grp != (int64_t)blockIdx.x) bar_sync(BAR_GROUP);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (sched.unit[c][i]) norm_store(v[i][0], v[i][1], dst[i], sign[i], true);   // uniform; the shuffle inside needs every lane
             __threadfence_block();
-            if (c < g.n_super || grp + gridDim.x < n_groups) bar_arrive(BAR_FULL + (gi & 1));   // (the CTA's very last batch is empty)
-            gi++;
+            bar_arrive(BAR_FULL + (c & 3));
         }
     }
 }
@@ -477,7 +488,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) dtw_pairs_stream4_kernel(DtwPairs
         producer_loop(a, n_groups, g, smem, sched);
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS));
-        consumer_loop(a, n_groups, g, smem);
+        consumer_loop(a, n_groups, g, smem, sched);
     }
 }
 
@@ -487,9 +498,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) dtw_pairs_stream4_kernel(DtwPairs
 // run super-step c (steps 2c-1, 2c; c = 0 is their prologue) and is first read in super-step c+1. Invariants, checked
 // here and again by tests/test_host_logic.py through rp_debug_stream4_schedule:
 //  (1) row pair k is stored before the step that reads it first, look-ahead included: batch <= (st_first(k) - 2) / 2;
-//  (2) ring slot k % 16 is free: the last read of row pair k-16 lies in a super-step before the batch's;
+//  (2) ring slot k % 16 is free: the last read of row pair k-16 lies DEPTH super-steps before the batch's (the
+//      producers run up to DEPTH super-steps ahead of the consumers);
 //  (3) the four quarters of window block B >= 4 are stored before the super-step of the step after which its warp
-//      switches to it, and after the super-step in which block B-2 (same staging slot) was read.
+//      switches to it, and DEPTH super-steps after the one in which block B-2 (same staging slot) was read.
+// Across groups nothing overlaps: the producers wait for the consumers' end-of-group signal before batch 0.
 bool build_stream4_schedule(int m, int n, int band, Stream4Sched* out, int* n_super_out) {
     Stream4Sched s;
     std::memset(&s, 0, sizeof(s));
@@ -514,12 +527,12 @@ bool build_stream4_schedule(int m, int n, int band, Stream4Sched* out, int* n_su
         int slot = 0;
         while (kf <= kmax && st_first(kf) <= 2 * c + 3) {
             if (slot == 4) return false;
-            if (kf > SLOTS && (st_last(kf - SLOTS) + 1) / 2 > c - 1) return false;   // (2)
+            if (kf > SLOTS && (st_last(kf - SLOTS) + 1) / 2 > c - DEPTH) return false;   // (2)
             s.unit[c][slot++] = (unsigned short)kf++;
         }
         while (qB < n_blocks && slot < 4 && c >= c_due(qB) - 2) {
             if (c > c_due(qB)) return false;                                            // (3) too late
-            if (qB - 2 >= NW && (s_sw(qB - 2) + 1) / 2 > c - 1) return false;           // (3) slot still in use
+            if (qB - 2 >= NW && (s_sw(qB - 2) + 1) / 2 > c - DEPTH) return false;       // (3) slot still in use
             s.unit[c][slot++] = (unsigned short)(0x8000u | (unsigned)(qB << 2) | (unsigned)qj);
             if (++qj == 4) {
                 qj = 0;
@@ -534,6 +547,47 @@ bool build_stream4_schedule(int m, int n, int band, Stream4Sched* out, int* n_su
     }
     for (int B = NW; B < n_blocks; B++)
         if (s_sw(B) < steps && B >= qB) return false;
+    // consumers: one control word per (warp, step)
+    auto mask = [&](int u, int c0) {
+        const int t = 2 * u - c0 + w - 2;
+        const int lo = std::min(std::max(7 - t, 0), 10), hi = std::min(std::max(7 - t + 2 * w, 0), 10);
+        return (1u << hi) - (1u << lo);
+    };
+    for (int wq = 0; wq < NW; wq++) {
+        int B = wq;
+        for (int st = 1; st <= steps; st++) {
+            const int u = st - SIGMA * B;
+            const int ufirst = std::max(1, 4 * B + 1 - w / 2), ulast = 4 * B + fin0;
+            if (B >= n_blocks || u < ufirst || u > ulast) continue;
+            const int c0 = B * CB + 1;
+            const unsigned M = mask(u, c0);
+            unsigned c = CTL_ACTIVE | (M << CTL_MASK_SHIFT) | ((unsigned)(u & 15) << CTL_SLOT_SHIFT);
+            if (u == ufirst) c |= CTL_FRESH;
+            if ((M & 0x1ffu) == 0x1ffu) c |= CTL_FULL;
+            if (B > 0) {
+                c |= CTL_HAS_LEFT;
+                if ((M >> 8) & 1u) c |= CTL_OK1;
+                if ((M >> 9) & 1u) c |= CTL_OK2;
+                if (u == ufirst && ((mask(u - 1, c0) >> 9) & 1u)) c |= CTL_OK2PREV;
+                if (u == 4 * (B - 1) + fin0 + 1) c |= CTL_DRAIN_RD;
+            }
+            if (u == ulast && st < steps) {
+                c |= CTL_SWITCH;
+                if (B + NW < n_blocks) c |= CTL_NEXT_EXISTS;
+                if ((B + NW) & 1) c |= CTL_NEXT_PARITY;
+                if (B + NW == n_blocks - 1) c |= CTL_NEXT_LAST;
+                s.ctl[wq][st] = c;
+                B += NW;
+                continue;
+            }
+            s.ctl[wq][st] = c;
+        }
+    }
+    {
+        const int Bl = n_blocks - 1, u = steps + 1 - SIGMA * Bl;
+        s.res_from_drain = Bl > 0 && u == 4 * (Bl - 1) + fin0 + 1;
+        s.res_slot = u & (XS - 1);
+    }
     if (out) *out = s;
     if (n_super_out) *n_super_out = n_super;
     return true;

@@ -61,8 +61,11 @@ cudaError_t launch_dtw_pairs_stream(const DtwPairsArgs& a, cudaStream_t stream);
 void set_dtw_stream_rows(int rows);
 // K2s v4 (dtw_stream4_kernel.cu): what its producer warps fetch in which batch; built on the host per (m, n, band).
 constexpr int STREAM4_MAX_BATCHES = 120;
+constexpr int STREAM4_MAX_STEPS = 2 * STREAM4_MAX_BATCHES;
 struct Stream4Sched {
-    unsigned short unit[STREAM4_MAX_BATCHES][4];
+    unsigned short unit[STREAM4_MAX_BATCHES][4];   // producers: what to fetch in batch c
+    unsigned ctl[4][STREAM4_MAX_STEPS + 2];        // consumers: control word of (warp, step), see CTL_* in the kernel
+    int res_from_drain, res_slot;                  // where the last block finds its left input after the last step
 };
 bool build_stream4_schedule(int m, int n, int band, Stream4Sched* out, int* n_super_out);
 
