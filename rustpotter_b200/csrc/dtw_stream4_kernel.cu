@@ -152,6 +152,16 @@ __device__ __forceinline__ void load_row(const float* __restrict__ p, f2 (&ar)[8
     }
 }
 
+// The same, predicated (warp-uniform predicate; keeps the caller's basic block in one piece).
+__device__ __forceinline__ void load_row_if(const float* __restrict__ p, f2 (&ar)[8], bool pred) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(p);
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p ld.shared.v2.u64 {%0, %1}, [%2];\n\t}"
+                     : "+l"(ar[2 * q]), "+l"(ar[2 * q + 1])
+                     : "r"(sa + 16 * q), "r"((int)pred));
+}
+
 // Half a 64-byte vector (v0, v1) -> scaled by sign / |vector| (the partner lane holds the other half; a zero
 // vector stays zero: similarity 0, distance 1) -> shared memory.
 __device__ __forceinline__ void norm_store(const ulonglong2& v0, const ulonglong2& v1, float* __restrict__ dst, float sign, bool store) {
@@ -192,11 +202,10 @@ __device__ __forceinline__ void half_step(const f2 (&ar)[8], const f2 (&bcol)[CB
 // of column c0-1 (the left neighbour's last).
 
 // One step of a block: template rows 2u-1 and 2u (rp0 = ring slot of row pair u, rp1 = of u+1) against the eight columns.
-// FULL: every cell is inside the band.
-template <bool FULL>
-__device__ __forceinline__ void block_step(const float* __restrict__ rp0, const float* __restrict__ rp1, unsigned M, float li1, float li2p, float li1_prev,
-                                           const f2 (&bcol)[CB][8], f2 (&ar1)[8], float (&D1)[CB], float (&D2)[CB], float (&cost2)[CB],
-                                           float& out1, float& out2, f2 one) {
+// full: every cell is inside the band (warp-uniform); otherwise M masks the costs (bits 7-j: row 2u-1, 8-j: row 2u).
+__device__ __forceinline__ void block_step(const float* __restrict__ rp0, const float* __restrict__ rp1, bool full, unsigned M, float li1,
+                                           float li2p, float li1_prev, const f2 (&bcol)[CB][8], f2 (&ar1)[8], float (&D1)[CB],
+                                           float (&D2)[CB], float (&cost2)[CB], float& out1, float& out2, f2 one) {
     f2 ar2[8], acc[CB];
     float cost1[CB];
     // ---- H1: dots of row 2u-1, DP of row 2u-2
@@ -204,13 +213,23 @@ __device__ __forceinline__ void block_step(const float* __restrict__ rp0, const 
     half_step(ar1, bcol, acc, cost2, D1, D2, li2p, li1_prev, one);
     out2 = D2[CB - 1];
 #pragma unroll
-    for (int j = 0; j < CB; j++) cost1[j] = (FULL || ((M >> (7 - j)) & 1u)) ? hsum(acc[j]) : INFINITY;
+    for (int j = 0; j < CB; j++) cost1[j] = hsum(acc[j]);
+    if (!full) {
+#pragma unroll
+        for (int j = 0; j < CB; j++)
+            if (!((M >> (7 - j)) & 1u)) cost1[j] = INFINITY;
+    }
     // ---- H2: dots of row 2u, DP of row 2u-1
     load_row(rp1, ar1);
     half_step(ar2, bcol, acc, cost1, D2, D1, li1, li2p, one);
     out1 = D1[CB - 1];
 #pragma unroll
-    for (int j = 0; j < CB; j++) cost2[j] = (FULL || ((M >> (8 - j)) & 1u)) ? hsum(acc[j]) : INFINITY;
+    for (int j = 0; j < CB; j++) cost2[j] = hsum(acc[j]);
+    if (!full) {
+#pragma unroll
+        for (int j = 0; j < CB; j++)
+            if (!((M >> (8 - j)) & 1u)) cost2[j] = INFINITY;
+    }
 }
 
 struct Geometry {
@@ -317,26 +336,21 @@ __device__ __forceinline__ void consumer_loop(const DtwPairsArgs& a, int64_t n_g
                 const unsigned so = ((ctl >> CTL_SLOT_SHIFT) & 15u) * (SLOT_F * 4);   // byte offset of row pair u in the ring
                 const unsigned so1 = (so + SLOT_F * 4) & (SLOTS * SLOT_F * 4 - 1);      // ... of row pair u+1
                 const unsigned xo = ((ctl >> CTL_SLOT_SHIFT) & 3u) * 256;               // ... of row pair u in the exchange array
-                if (ctl & CTL_FRESH) {   // fresh block: no look-ahead happened, and the step before it was skipped
-                    load_row(reinterpret_cast<const float*>(reinterpret_cast<const char*>(ring_p) + so), ar1);
-                    ok2_prev = (ctl & CTL_OK2PREV) != 0;
-                }
-                float shf1 = INFINITY, shf2 = INFINITY;
-                if (ctl & CTL_HAS_LEFT) {
-                    // D[2u-2][c0-1]: the left block's H1 of row pair u, or its drain if row pair u-1 was its last
-                    const float* x = reinterpret_cast<const float*>(reinterpret_cast<const char*>(xch_r) + xo);
-                    shf2 = (ctl & CTL_DRAIN_RD) ? xdrain_r[0] : x[0];
-                    shf1 = x[32];
-                }
+                const float* const rp0 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(ring_p) + so);
+                const float* const rp1 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(ring_p) + so1);
+                // fresh block: no look-ahead happened, and the step before it was skipped
+                load_row_if(rp0, ar1, (ctl & CTL_FRESH) != 0);
+                ok2_prev = (ctl & CTL_FRESH) ? (ctl & CTL_OK2PREV) != 0 : ok2_prev;
+                // D[2u-2][c0-1]: the left block's H1 of row pair u, or its drain if row pair u-1 was its last (block 0 reads
+                // the last warp's values and ignores them)
+                const float* x = reinterpret_cast<const float*>(reinterpret_cast<const char*>(xch_r) + xo);
+                const float xd = xdrain_r[0], x0 = x[0], shf1 = x[32];
+                const float shf2 = (ctl & CTL_DRAIN_RD) ? xd : x0;
                 const float li2p = ok2_prev ? shf2 : dseed;              // left input of row 2u-2 = diagonal input of row 2u-1
                 const float li1 = (ctl & CTL_OK1) ? shf1 : INFINITY;     // left input of row 2u-1 = diagonal input of row 2u
                 dseed = INFINITY;
-                const float* const rp0 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(ring_p) + so);
-                const float* const rp1 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(ring_p) + so1);
-                if (ctl & CTL_FULL)
-                    block_step<true>(rp0, rp1, 0u, li1, li2p, li1_prev, bcol, ar1, D1, D2, cost2, out1, out2, one);
-                else
-                    block_step<false>(rp0, rp1, (ctl >> CTL_MASK_SHIFT) & 0x3ffu, li1, li2p, li1_prev, bcol, ar1, D1, D2, cost2, out1, out2, one);
+                block_step(rp0, rp1, (ctl & CTL_FULL) != 0, (ctl >> CTL_MASK_SHIFT) & 0x3ffu, li1, li2p, li1_prev, bcol, ar1, D1, D2, cost2,
+                           out1, out2, one);
                 li1_prev = li1;
                 ok2_prev = (ctl & CTL_OK2) != 0;
                 {
