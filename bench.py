@@ -237,6 +237,7 @@ def cpu_baseline(rpw: bytes, audio_host: np.ndarray, target_seconds: float = 12.
     threads = os.cpu_count() or 1
     cfg = O.default_config()
     probe = min(audio_host.shape[0], threads)
+    O.run_streams(cfg, [rpw], audio_host[:probe], n_threads=threads, native=True)   # warm-up (library load, tables, threads)
     t0 = time.perf_counter()
     w0, _, _ = O.run_streams(cfg, [rpw], audio_host[:probe], n_threads=threads, native=True)
     dt = time.perf_counter() - t0

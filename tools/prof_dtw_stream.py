@@ -1,4 +1,4 @@
-"""ncu target: a few launches of the streaming DTW kernel on BASELINE configs[3]'s shape (fewer pairs)."""
+"""ncu target: a few launches of the streaming DTW kernel on BASELINE configs[3]'s shape."""
 import sys
 import torch
 sys.path.insert(0, ".")
