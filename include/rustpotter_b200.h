@@ -203,7 +203,9 @@ int rp_dtw_scores(const float* tmpl_dev, const int64_t* tmpl_off_dev, const int3
                   int64_t n_pairs, int d, int band, float score_ref, int cmn, float* out_dev, void* cuda_stream);
 /* Selects the DTW kernel variants (0 = automatic, 1 = generic reference-order kernels, 2 = tuned kernels,
  * 3 = tuned with the one-row-per-step streaming kernel, 4 = tuned with the two-windows-per-thread pipeline
- * kernel, 5 = tuned with the round-1 two-rows-per-step streaming kernel). For A/B measurements and parity tests. */
+ * kernel, 5 = tuned with the round-1 two-rows-per-step streaming kernel, 6 = tuned with the v3 streaming kernel
+ * (lanes of a warp as the systolic array); 0 and 2 take the v4 kernel (warps of a CTA as the systolic array,
+ * producer/consumer warpgroups) for windows 3..20). For A/B measurements and parity tests. */
 int rp_set_dtw_variant(int variant);
 /* Selects the MFCC kernel: 0 = automatic (two-frames-per-warp TMA-staged kernel where it applies), 1 = one frame
  * per warp. For A/B measurements and parity tests. */
@@ -228,6 +230,9 @@ typedef struct rp_wakeword_info {
  * 0x8000 | block << 2 | quarter (a quarter of a window block of 8 columns). Returns the number of batches, or 0
  * when the kernel does not take the shape. Exposed so that the schedule's invariants are tested without a GPU. */
 int rp_debug_stream4_schedule(int m, int n, int band, uint16_t* out, size_t out_cap);
+/* The same kernel's per-(warp, step) control words: out[warp * (steps + 1) + step], warp 0..3, step 1..steps (bit layout:
+ * CTL_* in dtw_stream4_kernel.cu). Returns steps, or 0 when the kernel does not take the shape. */
+int rp_debug_stream4_ctl(int m, int n, int band, uint32_t* out, size_t out_cap);
 /* Parses a .rpw buffer (WakewordV2 then WakewordRef, detector.rs:152-163). */
 int rp_wakeword_inspect(const uint8_t* buf, size_t len, rp_wakeword_info* info);
 /* Copies template t (t == -1: avg_features) of a .rpw buffer: name (RP_NAME_MAX bytes) and

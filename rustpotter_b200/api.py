@@ -85,7 +85,7 @@ EXPORTED = [
     "rp_batch_set_cuda_stream", "rp_batch_process", "rp_batch_update_config", "rp_batch_reset",
     "rp_batch_windows_scored", "rp_batch_n_streams", "rp_batch_max_mfcc_frames", "rp_batch_last_timings",
     "rp_batch_last_launches", "rp_batch_copy_last_scores", "rp_mfcc_frames", "rp_dtw_scores", "rp_set_dtw_variant", "rp_set_mfcc_variant", "rp_wakeword_inspect",
-    "rp_wakeword_template", "rp_host_replay", "rp_wakeword_build", "rp_wakeword_from_features", "rp_debug_stream4_schedule",
+    "rp_wakeword_template", "rp_host_replay", "rp_wakeword_build", "rp_wakeword_from_features", "rp_debug_stream4_schedule", "rp_debug_stream4_ctl",
 ]
 
 
@@ -411,6 +411,16 @@ def build_wakeword(name: str, samples: list[tuple[str, bytes]], mfcc_size: int =
 
 
 # ---------------------------------------------------------------- host-logic hooks (no GPU)
+def stream4_ctl(m: int, n: int, band: int):
+    """Control words of the streaming DTW kernel's consumer warps: uint32 [4][steps + 1] (column 0 unused), or None."""
+    L = lib()
+    L.rp_debug_stream4_ctl.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_size_t]
+    L.rp_debug_stream4_ctl.restype = C.c_int
+    out = np.zeros(4 * 256, np.uint32)
+    steps = L.rp_debug_stream4_ctl(m, n, band, out.ctypes.data_as(C.POINTER(C.c_uint32)), out.size)
+    return out[:4 * (steps + 1)].reshape(4, steps + 1).copy() if steps > 0 else None
+
+
 def stream4_schedule(m: int, n: int, band: int):
     """Producer schedule of the streaming DTW kernel: uint16 [batches][4], or None if the kernel does not take the shape."""
     L = lib()

@@ -527,6 +527,17 @@ int rp_debug_stream4_schedule(int m, int n, int band, uint16_t* out, size_t out_
     return n_super;
 }
 
+int rp_debug_stream4_ctl(int m, int n, int band, uint32_t* out, size_t out_cap) {
+    Stream4Sched s;
+    int n_super = 0;
+    if (!build_stream4_schedule(m, n, band, &s, &n_super)) return 0;
+    const int n_blocks = (n + 7) / 8, steps = m / 2 + 2 * (n_blocks - 1);
+    for (int w = 0; w < 4; w++)
+        for (int st = 0; st <= steps; st++)
+            if (out && (size_t)(w * (steps + 1) + st) < out_cap) out[w * (steps + 1) + st] = s.ctl[w][st];
+    return steps;
+}
+
 int rp_wakeword_inspect(const uint8_t* buf, size_t len, rp_wakeword_info* info) {
     if (!buf || !info) return RP_ERR_INVALID;
     return guarded((rp_handle*)nullptr, [&] {

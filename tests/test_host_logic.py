@@ -319,3 +319,59 @@ def test_stream4_schedule_invariants():
                             assert quarter_batch.get((B + 2, j), 1 << 30) - 2 >= S, (m, n, band, B, j)
                 checked += 1
     assert checked > 1500
+
+
+def test_stream4_control_words():
+    """The consumers' control words against the band geometry of dtw.rs:56-105 restated here: for every (warp, step) the
+    active flag, the cost mask (cells (r, c) with r - w <= c <= r + w - 1, 1 <= c <= .., r >= 1 handled by +inf
+    induction), the left-neighbour flags and the block sequence (b, b+4, ..) must match an independent derivation."""
+    from rustpotter_b200 import api
+    A, FRESH, FULL, SWITCH, OK1, OK2, OK2P, DRAIN, LEFT, NEXT, NPAR, NLAST = (1 << i for i in range(12))
+    n_checked = 0
+    for m, n, band in [(120, 100, 5), (100, 100, 5), (100, 100, 20), (121, 101, 5), (100, 120, 5), (41, 40, 3), (64, 72, 9),
+                       (33, 17, 16), (96, 97, 20), (300, 290, 12), (9, 8, 7), (2, 1, 5), (7, 3, 4)]:
+        ctl = api.stream4_ctl(m, n, band)
+        w = max(band, abs(m - n))
+        if not 3 <= w <= 20:
+            assert ctl is None
+            continue
+        assert ctl is not None, (m, n, band)
+        nb = (n + 7) // 8
+        steps = m // 2 + 2 * (nb - 1)
+        assert ctl.shape == (4, steps + 1)
+        in_band = lambda r, c: r - w <= c <= r + w - 1   # noqa: E731  (dtw.rs:73-78)
+        for wq in range(4):
+            B, prev_active = wq, False
+            for st in range(1, steps + 1):
+                c = int(ctl[wq, st])
+                u = st - 2 * B
+                rows = (2 * u - 1, 2 * u)
+                cols = range(8 * B + 1, 8 * B + 9)
+                any_cell = B < nb and u >= 1 and any(in_band(r, cc) for r in rows for cc in cols)
+                # active exactly while one of the block's 16 cells of this step lies inside the band
+                assert bool(c & A) == any_cell, (m, n, band, wq, st, B, u)
+                if not c & A:
+                    prev_active = False
+                    continue
+                n_checked += 1
+                assert bool(c & FRESH) == (not prev_active)
+                mask = (c >> 12) & 0x3ff
+                for j, cc in enumerate(cols):
+                    assert bool((mask >> (7 - j)) & 1) == in_band(rows[0], cc), (m, n, band, wq, st, j)
+                    assert bool((mask >> (8 - j)) & 1) == in_band(rows[1], cc), (m, n, band, wq, st, j)
+                assert bool(c & FULL) == all(in_band(r, cc) for r in rows for cc in cols)
+                assert bool(c & LEFT) == (B > 0)
+                assert bool(c & OK1) == (B > 0 and in_band(rows[0], 8 * B))
+                assert bool(c & OK2) == (B > 0 and in_band(rows[1], 8 * B))
+                if c & FRESH:
+                    assert bool(c & OK2P) == (B > 0 and in_band(rows[0] - 1, 8 * B))
+                assert ((c >> 22) & 15) == u % 16
+                prev_active = True
+                if c & SWITCH:
+                    assert st < steps
+                    # last step of the block: the next row pair has no cell of this block inside the band
+                    assert not any(in_band(r, cc) for r in (2 * u + 1, 2 * u + 2) for cc in cols)
+                    assert bool(c & NEXT) == (B + 4 < nb) and bool(c & NPAR) == bool((B + 4) & 1) and bool(c & NLAST) == (B + 4 == nb - 1)
+                    B += 4
+                    prev_active = False
+    assert n_checked > 2000
