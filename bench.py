@@ -271,6 +271,8 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
     n_streams = args.streams
+    if args.dtw_variant:
+        rp.set_dtw_variant(args.dtw_variant)
     rpw, audio = make_workload(torch, rp, device, n_streams, rank)
     audio_host = torch.empty(audio.shape, dtype=torch.float32, pin_memory=True)
     audio_host.copy_(audio)
@@ -427,6 +429,7 @@ def main():
     ap.add_argument("--streams", type=int, default=N_STREAMS, help="streams per GPU (default: BASELINE configs[1])")
     ap.add_argument("--ref-streams-per-thread", type=int, default=2)
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--dtw-variant", type=int, default=0, help="rp_set_dtw_variant for A/B measurements (default 0 = automatic)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -204,7 +204,8 @@ int rp_dtw_scores(const float* tmpl_dev, const int64_t* tmpl_off_dev, const int3
 /* Selects the DTW kernel variants (0 = automatic, 1 = generic reference-order kernels, 2 = tuned kernels,
  * 3 = tuned with the one-row-per-step streaming kernel, 4 = tuned with the two-windows-per-thread pipeline
  * kernel, 5 = tuned with the round-1 two-rows-per-step streaming kernel, 6 = tuned with the v3 streaming kernel
- * (lanes of a warp as the systolic array); 0 and 2 take the v4 kernel (warps of a CTA as the systolic array,
+ * (lanes of a warp as the systolic array), 7 = tuned with the pipeline kernel reading its templates from shared
+ * instead of constant memory; 0 and 2 take the v4 kernel (warps of a CTA as the systolic array,
  * producer/consumer warpgroups) for windows 3..20). For A/B measurements and parity tests. */
 int rp_set_dtw_variant(int variant);
 /* Selects the MFCC kernel: 0 = automatic (two-frames-per-warp TMA-staged kernel where it applies), 1 = one frame

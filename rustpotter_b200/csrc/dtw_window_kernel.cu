@@ -84,7 +84,25 @@ __device__ __forceinline__ float dot16(const Row16& a, const Row16& b) {
     return hsum(acc);
 }
 
-template <int W>
+// Unit-length template rows in constant memory (64 KB = 1024 rows): a template row is the same for every thread of a CTA, so it
+// comes through the constant cache into uniform registers instead of as four broadcast LDS.128 per warp and row — a quarter of
+// this kernel's shared-memory wavefronts, the pipe that bounds it (ncu r01: LSU data pipe 78 % busy). CT selects that path; the
+// launcher keeps the constant copy current and falls back to the shared-memory copy when the templates do not fit.
+constexpr int kConstRows = 1024;
+__constant__ float4 c_tmpl_unit[kConstRows * 4];
+
+__device__ __forceinline__ Row16 ldc_row(int f4_index) {
+    Row16 r;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const float4 v = c_tmpl_unit[f4_index + q];
+        r.p[2 * q] = pk(v.x, v.y);
+        r.p[2 * q + 1] = pk(v.z, v.w);
+    }
+    return r;
+}
+
+template <int W, bool CT>
 __global__ void __launch_bounds__(kThreads, 5) dtw_windows_d16_kernel(DtwWindowsArgs a, const float* __restrict__ tmpl_unit,
                                                                    int x_rows, int j_blocks) {
     constexpr int NB = 2 * W;  // band cells per row
@@ -106,6 +124,7 @@ __global__ void __launch_bounds__(kThreads, 5) dtw_windows_d16_kernel(DtwWindows
     const int64_t b = rest / j_blocks;
     const int j0 = a.first_window + jb * kNW;
     const int m = a.slot_len[s];
+    const int c_row0 = CT ? (int)(a.slot_off[s] >> 2) : 0;   // float4 index of the slot's first row in c_tmpl_unit
 
     // ---- stage the frame tile and the template in shared memory
     {
@@ -118,8 +137,10 @@ __global__ void __launch_bounds__(kThreads, 5) dtw_windows_d16_kernel(DtwWindows
             if (u < avail) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)u * kD) + q);
             *reinterpret_cast<float4*>(Xs + u * kXS + 4 * q) = v;
         }
-        const float4* ts = reinterpret_cast<const float4*>(tmpl_unit + a.slot_off[s]);
-        for (int i = tid; i < m * 4; i += kThreads) reinterpret_cast<float4*>(Ts)[i] = __ldg(ts + i);
+        if (!CT) {
+            const float4* ts = reinterpret_cast<const float4*>(tmpl_unit + a.slot_off[s]);
+            for (int i = tid; i < m * 4; i += kThreads) reinterpret_cast<float4*>(Ts)[i] = __ldg(ts + i);
+        }
     }
     __syncthreads();
 
@@ -207,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 5) dtw_windows_d16_kernel(DtwWindows
             const int r = r0 + k + 1;  // r % NB == (k + 1) % NB because r0 is a multiple of NB
             if (r <= last_row) {       // uniform over the CTA
                 float* G = Gs + (r & 1) * GS;
-                const Row16 ar = lds_row(Ts + (r - 1) * kD);  // broadcast
+                const Row16 ar = CT ? ldc_row(c_row0 + (r - 1) * 4) : lds_row(Ts + (r - 1) * kD);  // the same for the whole CTA
                 float A = 0.f;
                 if (dp) {
                     // own new column c = r+W-1 <-> frame u = t + r + W - 2
@@ -489,11 +510,22 @@ __global__ void __launch_bounds__(kThreads2) dtw_windows_d16x2_kernel(DtwWindows
 
 }  // namespace
 
-int g_window_kernel = 0;  // 0/1 = one window per thread (default), 2 = two windows per thread (A/B measurements)
+int g_window_kernel = 0;  // 0/1 = one window per thread (default), 2 = two windows per thread, 3 = one window per thread with the
+                          // templates in shared memory even when they fit constant memory (A/B measurements)
 void set_dtw_window_kernel(int v) { g_window_kernel = v; }
 
-// Unit-normalised templates are prepared by the engine (tmpl_unit has the layout of a.tmpl).
-cudaError_t launch_dtw_windows_d16(const DtwWindowsArgs& a, const float* tmpl_unit, cudaStream_t stream) {
+// Unit-normalised templates are prepared by the engine (tmpl_unit has the layout of a.tmpl; tmpl_floats of them, tmpl_version
+// changes whenever their contents do).
+namespace {
+struct ConstOwner {
+    const float* src = nullptr;
+    uint64_t version = 0;
+};
+ConstOwner g_const_owner[64];   // per device: whose templates c_tmpl_unit holds
+}  // namespace
+
+cudaError_t launch_dtw_windows_d16(const DtwWindowsArgs& a, const float* tmpl_unit, size_t tmpl_floats, uint64_t tmpl_version,
+                                   cudaStream_t stream) {
     if (a.d != kD || a.band != 5) return cudaErrorInvalidValue;
     constexpr int W = 5;
     const int j_blocks = (a.n_new - a.first_window + kNW - 1) / kNW;
@@ -515,9 +547,28 @@ cudaError_t launch_dtw_windows_d16(const DtwWindowsArgs& a, const float* tmpl_un
     const size_t bytes = ((size_t)x_rows * kXS + (size_t)a.max_len * kD + 2 * (kNW + 2 * W) + (kThreads / 16 + 1) * kD +
                           (size_t)p_rows * kD) * sizeof(float);
     if (bytes > 200 * 1024) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(dtw_windows_d16_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool ct = g_window_kernel != 3 && tmpl_floats > 0 && tmpl_floats <= (size_t)kConstRows * kD && dev >= 0 && dev < 64;
+    if (ct) {
+        ConstOwner& o = g_const_owner[dev];
+        if (o.src != tmpl_unit || o.version != tmpl_version) {
+            // another template set owns the constant copy: kernels that still read it (any stream) must finish first
+            cudaError_t e0 = cudaDeviceSynchronize();
+            if (e0 != cudaSuccess) return e0;
+            e0 = cudaMemcpyToSymbolAsync(c_tmpl_unit, tmpl_unit, tmpl_floats * sizeof(float), 0, cudaMemcpyDeviceToDevice, stream);
+            if (e0 != cudaSuccess) return e0;
+            o.src = tmpl_unit;
+            o.version = tmpl_version;
+        }
+        cudaError_t e = cudaFuncSetAttribute(dtw_windows_d16_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        dtw_windows_d16_kernel<W, true><<<(unsigned)ctas, kThreads, bytes, stream>>>(a, tmpl_unit, x_rows, j_blocks);
+        return cudaGetLastError();
+    }
+    cudaError_t e = cudaFuncSetAttribute(dtw_windows_d16_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
-    dtw_windows_d16_kernel<W><<<(unsigned)ctas, kThreads, bytes, stream>>>(a, tmpl_unit, x_rows, j_blocks);
+    dtw_windows_d16_kernel<W, false><<<(unsigned)ctas, kThreads, bytes, stream>>>(a, tmpl_unit, x_rows, j_blocks);
     return cudaGetLastError();
 }
 

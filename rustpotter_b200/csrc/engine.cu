@@ -1,5 +1,7 @@
 #include "engine.h"
 
+#include <atomic>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -135,6 +137,9 @@ void Engine::configure(const WakewordSet& ws, const rp_config& cfg) {
             for (int k = 0; k < d_; k++) unit[r + k] = tmpl[r + k] * inv;
         }
         upload(tmpl_unit_, unit, stream_, "unit templates");
+        tmpl_unit_floats_ = unit.size();
+        static std::atomic<uint64_t> next_version{1};
+        tmpl_version_ = next_version++;
     }
     upload(slot_off_, off, stream_, "slot offsets");
     upload(slot_len_, len, stream_, "slot lengths");
@@ -333,7 +338,7 @@ void Engine::process(const float* audio, int64_t S, bool on_device, bool want_va
         wa.scores = tscore_.as<float>() + b0 * (int64_t)n_new * n_slots_;
         wa.first_window = std::min(std::max(first_window, 0), n_new);
         if (d_ == 16 && band_ == 5 && dtw_variant_ != 1)
-            cuda_check(launch_dtw_windows_d16(wa, tmpl_unit_.as<float>(), stream_), "dtw window kernel");
+            cuda_check(launch_dtw_windows_d16(wa, tmpl_unit_.as<float>(), tmpl_unit_floats_, tmpl_version_, stream_), "dtw window kernel");
         else
             cuda_check(launch_dtw_windows_generic(wa, stream_), "dtw kernel");
         JudgeArgs ja;

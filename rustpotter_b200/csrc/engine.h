@@ -104,6 +104,8 @@ class Engine {
     int band_ = 5, score_mode_ = 1;
     float score_ref_ = 0.22f;
     DeviceBuffer tmpl_, tmpl_unit_, slot_off_, slot_len_, metas_;
+    size_t tmpl_unit_floats_ = 0;   // floats in tmpl_unit_
+    uint64_t tmpl_version_ = 0;     // changes with every upload of the templates (the window kernel's constant-memory copy follows it)
     // MFCC tables on device
     DeviceMfccTables mfcc_tables_;
     // per-stream state

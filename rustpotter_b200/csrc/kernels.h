@@ -91,8 +91,9 @@ struct DtwWindowsArgs {
 cudaError_t launch_dtw_windows_generic(const DtwWindowsArgs& a, cudaStream_t stream);
 // Tuned variant for d == 16, band == 5 (dtw_window_kernel.cu). tmpl_unit: the templates of a.tmpl with every row
 // scaled to unit length (zero rows stay zero), same offsets.
-cudaError_t launch_dtw_windows_d16(const DtwWindowsArgs& a, const float* tmpl_unit, cudaStream_t stream);
-void set_dtw_window_kernel(int v);  // 0/1 = one window per thread (default), 2 = two windows per thread
+cudaError_t launch_dtw_windows_d16(const DtwWindowsArgs& a, const float* tmpl_unit, size_t tmpl_floats, uint64_t tmpl_version,
+                                   cudaStream_t stream);
+void set_dtw_window_kernel(int v);  // 0/1 = one window per thread (default), 2 = two windows per thread, 3 = templates from shared memory
 
 // K3: judge every window, append detections to a compact hit list.
 // hit record (floats/ints, stride = 5 + max_templates): [stream, frame, wakeword, avg_score, score, scores...]
