@@ -27,6 +27,8 @@
 #include <cfloat>
 #include <cmath>
 
+#include <mutex>
+
 #include "kernels.h"
 
 namespace rp {
@@ -517,11 +519,47 @@ void set_dtw_window_kernel(int v) { g_window_kernel = v; }
 // Unit-normalised templates are prepared by the engine (tmpl_unit has the layout of a.tmpl; tmpl_floats of them, tmpl_version
 // changes whenever their contents do).
 namespace {
+// Whose templates c_tmpl_unit holds, per device. Handles are independent objects that may be driven from different host
+// threads and streams, so ownership changes hands carefully: under a lock, after every kernel on the device has finished, and
+// only once the current owner has been silent for kTakeOver launches of the challenger (which scores from shared memory meanwhile).
 struct ConstOwner {
     const float* src = nullptr;
     uint64_t version = 0;
+    const float* challenger = nullptr;
+    uint64_t challenger_version = 0;
+    int challenger_launches = 0;
 };
-ConstOwner g_const_owner[64];   // per device: whose templates c_tmpl_unit holds
+constexpr int kTakeOver = 64;
+ConstOwner g_const_owner[64];
+std::mutex g_const_mu;
+
+// Called with g_const_mu held; true: the constant copy is this template set's and stays so until the lock is released.
+bool const_templates_mine(int dev, const float* tmpl_unit, size_t tmpl_floats, uint64_t version, cudaStream_t stream, cudaError_t* err) {
+    ConstOwner& o = g_const_owner[dev];
+    if (o.src == tmpl_unit && o.version == version) {
+        o.challenger = nullptr;
+        return true;
+    }
+    if (o.src != nullptr) {
+        if (o.challenger == tmpl_unit && o.challenger_version == version) {
+            o.challenger_launches++;
+        } else {
+            o.challenger = tmpl_unit;
+            o.challenger_version = version;
+            o.challenger_launches = 1;
+        }
+        if (o.challenger_launches < kTakeOver) return false;
+        // kernels of the previous owner (any stream) may still read the constant copy
+        *err = cudaDeviceSynchronize();
+        if (*err != cudaSuccess) return false;
+    }
+    *err = cudaMemcpyToSymbolAsync(c_tmpl_unit, tmpl_unit, tmpl_floats * sizeof(float), 0, cudaMemcpyDeviceToDevice, stream);
+    if (*err != cudaSuccess) return false;
+    o.src = tmpl_unit;
+    o.version = version;
+    o.challenger = nullptr;
+    return true;
+}
 }  // namespace
 
 cudaError_t launch_dtw_windows_d16(const DtwWindowsArgs& a, const float* tmpl_unit, size_t tmpl_floats, uint64_t tmpl_version,
@@ -549,18 +587,12 @@ cudaError_t launch_dtw_windows_d16(const DtwWindowsArgs& a, const float* tmpl_un
     if (bytes > 200 * 1024) return cudaErrorInvalidValue;
     int dev = 0;
     cudaGetDevice(&dev);
-    const bool ct = g_window_kernel != 3 && tmpl_floats > 0 && tmpl_floats <= (size_t)kConstRows * kD && dev >= 0 && dev < 64;
+    std::lock_guard<std::mutex> lock(g_const_mu);   // (the launch below happens while the ownership is known)
+    cudaError_t e0 = cudaSuccess;
+    const bool ct = g_window_kernel != 3 && tmpl_floats > 0 && tmpl_floats <= (size_t)kConstRows * kD && dev >= 0 && dev < 64 &&
+                    const_templates_mine(dev, tmpl_unit, tmpl_floats, tmpl_version, stream, &e0);
+    if (e0 != cudaSuccess) return e0;
     if (ct) {
-        ConstOwner& o = g_const_owner[dev];
-        if (o.src != tmpl_unit || o.version != tmpl_version) {
-            // another template set owns the constant copy: kernels that still read it (any stream) must finish first
-            cudaError_t e0 = cudaDeviceSynchronize();
-            if (e0 != cudaSuccess) return e0;
-            e0 = cudaMemcpyToSymbolAsync(c_tmpl_unit, tmpl_unit, tmpl_floats * sizeof(float), 0, cudaMemcpyDeviceToDevice, stream);
-            if (e0 != cudaSuccess) return e0;
-            o.src = tmpl_unit;
-            o.version = tmpl_version;
-        }
         cudaError_t e = cudaFuncSetAttribute(dtw_windows_d16_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
         dtw_windows_d16_kernel<W, true><<<(unsigned)ctas, kThreads, bytes, stream>>>(a, tmpl_unit, x_rows, j_blocks);

@@ -490,6 +490,37 @@ def test_window_scores_tuned_vs_generic_vs_oracle(lengths):
             assert rel.max() < tol, (lengths, b, variant, rel.max(), np.unravel_index(rel.argmax(), rel.shape))
 
 
+def test_window_kernel_constant_templates_change_hands():
+    """The tuned window kernel reads its template rows from a constant-memory copy that belongs to ONE template set per
+    device; another handle scores from shared memory until the owner has been silent for 64 of its launches, then takes
+    over. Two handles with different wakewords, alternating and then one alone for > 64 launches: every dense score
+    tensor must equal the shared-memory-only variant (7) bit for bit."""
+    rpw_a, _ = make_wakeword(O, name="alpha", d=16, seed=300, lengths=(90, 100, 95))
+    rpw_b, _ = make_wakeword(O, name="beta", d=16, seed=301, lengths=(80, 120, 101, 77))
+    n_chunks = 4
+    chunks = [synth_audio(2, n_chunks * 480, seed=900 + i) for i in range(80)]
+
+    def run(variant):
+        rp.set_dtw_variant(variant)
+        a, b = rp.RustpotterBatch(2), rp.RustpotterBatch(2)
+        a.add_wakeword_from_buffer("a", rpw_a)
+        b.add_wakeword_from_buffer("b", rpw_b)
+        out = []
+        for i, au in enumerate(chunks):
+            if i < 10 or i >= 76:           # alternate: a owns the constant copy, b challenges
+                a.process(au)
+                out.append(a.last_scores(n_chunks * 3, 4).copy())
+            b.process(au)                    # 66 launches of b alone in the middle: it takes the copy over
+            out.append(b.last_scores(n_chunks * 3, 5).copy())
+        rp.set_dtw_variant(0)
+        return out
+
+    got, want = run(0), run(7)
+    assert len(got) == len(want)
+    for g, w in zip(got[24:], want[24:]):   # (the first calls have windows no detector scores yet: entries not written)
+        assert np.array_equal(g, w, equal_nan=True)
+
+
 def test_batch_stream_groups_do_not_change_results(monkeypatch):
     """The engine pipelines the batch in groups of streams (H2D of group g+1 under the kernels of
     group g); results must not depend on the group size. Host (pinned and pageable) and device audio."""
