@@ -9,9 +9,10 @@
 // previous row interleaved), but the systolic array is turned by 90 degrees and the CTA is split in roles:
 //
 //  * CONSUMER warps 0..3: what v3 mapped to the five LANES of a pair is mapped to four WARPS, and a lane is
-//    one pair of a group of 32. Block index, band mask, block switches are warp-uniform: no divergence, and
-//    steps whose 8x2 cells lie fully inside the band take a code path without any mask (15 of a block's 24
-//    steps at window 20). All 32 lanes work (v3: 30); a warp whose block is outside the band skips the step
+//    one pair of a group of 32. Block index, band mask, block switches are warp-uniform and come from a
+//    host-built table of control words: no divergence, one straight-line step body of 277 instructions (128
+//    FFMA2; the band mask is applied with R2P + FSEL, measured faster than a second, mask-free body for the 15
+//    of a block's 24 steps that lie fully inside the band). All 32 lanes work (v3: 30); a warp whose block is outside the band skips the step
 //    instead of issuing masked work; the pipeline fill/drain of a group costs idle WARPS, which the second
 //    resident CTA fills, instead of idle issue slots. Cells issued per pair: 4656 (3810 useful), v3: 6144.
 //    Block b runs two steps behind block b-1, so one warp owns blocks b, b+4, b+8, .. back to back, boundary
@@ -27,7 +28,9 @@
 //  * A block switch is 32 conflict-free LDS.128 (the staged block is already negated and normalised).
 //
 // Shapes: d == 16, uniform m >= 2, n >= 1, no CMN, 3 <= window = max(band, |m-n|) <= 20, at most 238 steps.
-// Everything else takes the older kernels.
+// Everything else takes the older kernels. Measured (B200, 1 M pairs 120x16 / 100x16): 6.46 ms = 2.18 TB/s algorithmic;
+// what bounds it (FP32 issue, two consumer warps per scheduler) and the variants that were measured and dropped are in
+// DESIGN.md section 6 and profiles/r01_SUMMARY.md.
 #include <cfloat>
 #include <cmath>
 #include <algorithm>
