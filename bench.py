@@ -259,8 +259,24 @@ def dist_setup(n_gpus: int):
     return rank, world, local
 
 
+def _stdout_to_stderr() -> int:
+    """Everything but the JSON line goes to stderr: NCCL prints its version banner to stdout when the first
+    communicator is created, and the contract is ONE line on stdout."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def _restore_stdout(saved: int) -> None:
+    sys.stdout.flush()
+    os.dup2(saved, 1)
+    os.close(saved)
+
+
 def run_ours(args):
     import torch
+    saved_stdout = _stdout_to_stderr()
 
     import rustpotter_b200 as rp
     rank, world, local = dist_setup(args.gpus)
@@ -376,7 +392,9 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             n_cpu = min(n_streams, 2048)
             line["cpu_baseline"] = cpu_baseline(rpw, audio_host[:n_cpu].numpy())
-        print(json.dumps(line))
+        _restore_stdout(saved_stdout)
+        print(json.dumps(line), flush=True)
+        saved_stdout = _stdout_to_stderr()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
