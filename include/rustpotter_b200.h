@@ -138,9 +138,15 @@ typedef struct rp_batch_detection {
 } rp_batch_detection;
 
 int rp_batch_create(const rp_config* cfg, int64_t n_streams, int device, rp_batch** out);
+/* The same over several devices: stream range [i*n/G, (i+1)*n/G) lives on device_ids[i]; templates and
+ * tables are replicated, nothing is exchanged between devices (streams are independent `Rustpotter`s), one host thread
+ * per device drives its range inside every call. A multi-device batch takes HOST audio. */
+int rp_batch_create_multi(const rp_config* cfg, int64_t n_streams, const int* device_ids, int n_devices, rp_batch** out);
+int rp_batch_n_devices(const rp_batch* b);
 void rp_batch_destroy(rp_batch* b);
 int rp_batch_add_wakeword_from_buffer(rp_batch* b, const char* key, const uint8_t* buf, size_t len);
 int rp_batch_add_wakeword_from_file(rp_batch* b, const char* key, const char* path);
+int rp_batch_remove_wakeword(rp_batch* b, const char* key);   /* Rustpotter::remove_wakeword  detector.rs:180 */
 int rp_batch_remove_wakewords(rp_batch* b);
 /* Use the caller's cudaStream_t for every launch/copy of this batch (default: a private stream). */
 int rp_batch_set_cuda_stream(rp_batch* b, void* cuda_stream);
@@ -151,6 +157,17 @@ int rp_batch_set_cuda_stream(rp_batch* b, void* cuda_stream);
  * *dets / *n_dets: detections in (stream, chunk) order, storage owned by the batch until the next call. */
 int rp_batch_process(rp_batch* b, const float* audio, int64_t samples_per_stream, int audio_on_device,
                      const rp_batch_detection** dets, int64_t* n_dets);
+/* Rustpotter::process_samples<T> (detector.rs:245-256) for every stream: `audio` is [n_streams][samples_per_stream]
+ * samples of `sample_format` (RP_FMT_*: int8_t / int16_t / int32_t / float, native byte order) with the config's
+ * `channels` interleaved (channel 0 is used, encoder.rs:41-48); samples_per_stream counts interleaved samples and must
+ * be a multiple of 480 * channels. Sample::into_f32 (audio_types.rs:98-137) runs on the device, so an i16 source costs
+ * half the host-to-device bytes of f32. Otherwise as rp_batch_process. */
+int rp_batch_process_samples(rp_batch* b, const void* audio, int sample_format, int64_t samples_per_stream, int audio_on_device,
+                             const rp_batch_detection** dets, int64_t* n_dets);
+/* Rustpotter::process_bytes (detector.rs:234-244) for every stream: raw bytes in the config's sample_format /
+ * endianness / channels; bytes_per_stream must be a multiple of rp_get_bytes_per_frame(). */
+int rp_batch_process_bytes(rp_batch* b, const uint8_t* audio_bytes, int64_t bytes_per_stream, int audio_on_device,
+                           const rp_batch_detection** dets, int64_t* n_dets);
 int rp_batch_update_config(rp_batch* b, const rp_config* cfg);
 void rp_batch_reset(rp_batch* b);
 uint64_t rp_batch_windows_scored(const rp_batch* b);      /* sum over streams, cumulative */
@@ -162,11 +179,17 @@ int rp_batch_max_mfcc_frames(const rp_batch* b);          /* longest template ov
 int rp_batch_last_timings(const rp_batch* b, float* ms, int cap);
 /* Number of kernels launched by the last rp_batch_process. */
 int rp_batch_last_launches(const rp_batch* b);
+/* Avg gate of the last call (wakeword_comp.rs:85-94: templates are scored only when the avg_features score reaches
+ * avg_threshold; here per tile of 128 consecutive windows of one stream and wakeword): tiles examined and tiles with a
+ * passing window. 0 / 0 when the gate did not run (dense mode, no avg_features, generic kernel). */
+int rp_batch_last_gate_stats(const rp_batch* b, int64_t* tiles, int64_t* passed);
 /* Parity-test tap: copies the dense per-window scores of the last rp_batch_process to host memory,
  * [n_streams][n_new][n_slots] (n_new = samples_per_stream/160 windows, one per new 10 ms hop; slots per
  * wakeword in insertion order: [avg_features score if present], template 0..T-1). These are the raw
- * MfccComparator::compare outputs BEFORE the avg gate / threshold; windows the detector would not score
- * (stream start, after a reset) are present but meaningless. Returns floats written or <0. */
+ * MfccComparator::compare outputs BEFORE the avg gate / threshold; windows no stream of the batch could score
+ * (the leading hops after a reset of the whole batch) and template scores the avg gate skipped read as NaN, other
+ * windows the detector would not score (stream start, after a reset of one stream) are present but meaningless.
+ * Returns floats written or <0. */
 int64_t rp_batch_copy_last_scores(const rp_batch* b, float* out_host, int64_t cap_floats, int32_t* n_new, int32_t* n_slots);
 
 /* =============================================================================================
@@ -202,12 +225,15 @@ int rp_dtw_scores(const float* tmpl_dev, const int64_t* tmpl_off_dev, const int3
                   const float* win_dev, const int64_t* win_off_dev, const int32_t* win_len_dev, int win_len_uniform,
                   int64_t n_pairs, int d, int band, float score_ref, int cmn, float* out_dev, void* cuda_stream);
 /* Selects the DTW kernel variants (0 = automatic, 1 = generic reference-order kernels, 2 = tuned kernels,
- * 3 = tuned with the one-row-per-step streaming kernel, 4 = tuned with the two-windows-per-thread pipeline
- * kernel, 5 = tuned with the round-1 two-rows-per-step streaming kernel, 6 = tuned with the v3 streaming kernel
+ * 3 = tuned with the one-row-per-step streaming kernel, 4 = (retired) same as 2, 5 = tuned with the round-1 two-rows-per-step streaming kernel, 6 = tuned with the v3 streaming kernel
  * (lanes of a warp as the systolic array), 7 = tuned with the pipeline kernel reading its templates from shared
  * instead of constant memory; 0 and 2 take the v4 kernel (warps of a CTA as the systolic array,
  * producer/consumer warpgroups) for windows 3..20). For A/B measurements and parity tests. */
 int rp_set_dtw_variant(int variant);
+/* Avg gate of the batched window scorer: 1 / -1 (default) = score avg_features first and the templates only where the
+ * gate can pass, as the reference does; 0 = every template of every window (dense score tensor; parity taps, A/B). The
+ * detections are identical in both modes. Process-wide debug knob like rp_set_dtw_variant. */
+int rp_set_avg_gate(int mode);
 /* Selects the MFCC kernel: 0 = automatic (two-frames-per-warp TMA-staged kernel where it applies), 1 = one frame
  * per warp. For A/B measurements and parity tests. */
 int rp_set_mfcc_variant(int variant);

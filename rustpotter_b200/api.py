@@ -84,7 +84,8 @@ EXPORTED = [
     "rp_batch_add_wakeword_from_buffer", "rp_batch_add_wakeword_from_file", "rp_batch_remove_wakewords",
     "rp_batch_set_cuda_stream", "rp_batch_process", "rp_batch_update_config", "rp_batch_reset",
     "rp_batch_windows_scored", "rp_batch_n_streams", "rp_batch_max_mfcc_frames", "rp_batch_last_timings",
-    "rp_batch_last_launches", "rp_batch_copy_last_scores", "rp_mfcc_frames", "rp_dtw_scores", "rp_set_dtw_variant", "rp_set_mfcc_variant", "rp_wakeword_inspect",
+    "rp_batch_last_launches", "rp_batch_copy_last_scores", "rp_batch_create_multi", "rp_batch_n_devices",
+    "rp_batch_remove_wakeword", "rp_batch_process_samples", "rp_batch_process_bytes", "rp_batch_last_gate_stats", "rp_set_avg_gate", "rp_mfcc_frames", "rp_dtw_scores", "rp_set_dtw_variant", "rp_set_mfcc_variant", "rp_wakeword_inspect",
     "rp_wakeword_template", "rp_host_replay", "rp_wakeword_build", "rp_wakeword_from_features", "rp_debug_stream4_schedule", "rp_debug_stream4_ctl",
 ]
 
@@ -125,7 +126,14 @@ def lib() -> C.CDLL:
     L.rp_windows_scored.restype = C.c_uint64
     L.rp_windows_scored.argtypes = [vp]
     L.rp_batch_create.argtypes = [cfgp, C.c_int64, C.c_int, C.POINTER(vp)]
+    L.rp_batch_create_multi.argtypes = [cfgp, C.c_int64, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    L.rp_batch_n_devices.argtypes = [vp]
     L.rp_batch_destroy.argtypes = [vp]
+    L.rp_batch_remove_wakeword.argtypes = [vp, C.c_char_p]
+    L.rp_batch_process_samples.argtypes = [vp, vp, C.c_int, C.c_int64, C.c_int, C.POINTER(C.POINTER(CBatchDetection)), C.POINTER(C.c_int64)]
+    L.rp_batch_process_bytes.argtypes = [vp, vp, C.c_int64, C.c_int, C.POINTER(C.POINTER(CBatchDetection)), C.POINTER(C.c_int64)]
+    L.rp_batch_last_gate_stats.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.rp_set_avg_gate.argtypes = [C.c_int]
     L.rp_batch_add_wakeword_from_buffer.argtypes = [vp, C.c_char_p, u8p, C.c_size_t]
     L.rp_batch_add_wakeword_from_file.argtypes = [vp, C.c_char_p, C.c_char_p]
     L.rp_batch_remove_wakewords.argtypes = [vp]
@@ -265,12 +273,18 @@ class Rustpotter:
 class RustpotterBatch:
     """N independent streams scored together on one device (rp_batch_*)."""
 
-    def __init__(self, n_streams: int, config: Config | None = None, device: int = 0):
+    def __init__(self, n_streams: int, config: Config | None = None, device: int = 0, devices=None):
+        """devices: list of CUDA device ids -> rp_batch_create_multi (streams sharded contiguously, host audio only)."""
         self._L = lib()
         self._h = C.c_void_p()
         cfg = config if config is not None else default_config()
-        _check(self._L.rp_batch_create(C.byref(cfg), n_streams, device, C.byref(self._h)))
+        if devices is None:
+            _check(self._L.rp_batch_create(C.byref(cfg), n_streams, device, C.byref(self._h)))
+        else:
+            ids = (C.c_int * len(devices))(*devices)
+            _check(self._L.rp_batch_create_multi(C.byref(cfg), n_streams, ids, len(devices), C.byref(self._h)))
         self.n_streams = n_streams
+        self.channels = int(cfg.channels)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -285,28 +299,66 @@ class RustpotterBatch:
     def add_wakeword_from_file(self, key: str, path: str):
         _check(self._L.rp_batch_add_wakeword_from_file(self._h, key.encode(), path.encode()), self._h)
 
+    def remove_wakeword(self, key: str) -> bool:
+        return bool(_check(self._L.rp_batch_remove_wakeword(self._h, key.encode()), self._h))
+
     def remove_wakewords(self) -> bool:
         return bool(_check(self._L.rp_batch_remove_wakewords(self._h), self._h))
+
+    def n_devices(self) -> int:
+        return self._L.rp_batch_n_devices(self._h)
 
     def set_cuda_stream(self, stream_handle: int):
         _check(self._L.rp_batch_set_cuda_stream(self._h, C.c_void_p(stream_handle)), self._h)
 
-    def process_ptr(self, ptr: int, samples_per_stream: int, on_device: bool):
-        """audio at raw address `ptr` ([n_streams][samples_per_stream] f32)."""
-        dets = C.POINTER(CBatchDetection)()
-        n = C.c_int64()
-        _check(self._L.rp_batch_process(self._h, C.c_void_p(ptr), samples_per_stream, int(on_device), C.byref(dets), C.byref(n)), self._h)
+    def _dets(self, dets, n):
         return [(int(dets[i].stream), int(dets[i].chunk), dets[i].det.to_dict()) for i in range(n.value)]
 
+    def process_ptr(self, ptr: int, samples_per_stream: int, on_device: bool, fmt: str = "f32"):
+        """audio at raw address `ptr` ([n_streams][samples_per_stream] of `fmt`: i8/i16/i32/f32, interleaved channels)."""
+        dets = C.POINTER(CBatchDetection)()
+        n = C.c_int64()
+        if fmt == "f32" and self.channels == 1:
+            _check(self._L.rp_batch_process(self._h, C.c_void_p(ptr), samples_per_stream, int(on_device), C.byref(dets), C.byref(n)), self._h)
+        else:
+            _check(self._L.rp_batch_process_samples(self._h, C.c_void_p(ptr), SAMPLE_FORMATS[fmt], samples_per_stream, int(on_device),
+                                                    C.byref(dets), C.byref(n)), self._h)
+        return self._dets(dets, n)
+
     def process(self, audio):
-        """audio: host numpy [n_streams][S] float32, or a torch tensor (CPU pinned/pageable or CUDA)."""
+        """process_samples<T> for every stream. audio: [n_streams][S] int8/int16/int32/float32 — a host numpy array or a
+        torch tensor (CPU pinned/pageable or CUDA)."""
         if hasattr(audio, "data_ptr"):  # torch tensor
-            assert audio.dtype.is_floating_point and audio.element_size() == 4 and audio.is_contiguous()
-            assert audio.shape[0] == self.n_streams
-            return self.process_ptr(audio.data_ptr(), int(audio.shape[1]), audio.is_cuda)
-        a = np.ascontiguousarray(audio, dtype=np.float32)
+            import torch
+            fmt = {torch.float32: "f32", torch.int16: "i16", torch.int32: "i32", torch.int8: "i8"}[audio.dtype]
+            assert audio.is_contiguous() and audio.shape[0] == self.n_streams
+            return self.process_ptr(audio.data_ptr(), int(audio.shape[1]), audio.is_cuda, fmt)
+        a = np.ascontiguousarray(audio)
+        fmt = {np.dtype(np.float32): "f32", np.dtype(np.int16): "i16", np.dtype(np.int32): "i32", np.dtype(np.int8): "i8"}.get(a.dtype)
+        if fmt is None:
+            a, fmt = np.ascontiguousarray(audio, dtype=np.float32), "f32"
         assert a.shape[0] == self.n_streams
-        return self.process_ptr(a.ctypes.data, a.shape[1], False)
+        return self.process_ptr(a.ctypes.data, a.shape[1], False, fmt)
+
+    def process_bytes(self, audio_bytes, bytes_per_stream: int | None = None, on_device: bool = False):
+        """process_bytes for every stream: raw bytes in the config's sample format / endianness / channels.
+        audio_bytes: bytes-like / uint8 numpy [n_streams][bytes_per_stream], or a raw address with bytes_per_stream."""
+        dets = C.POINTER(CBatchDetection)()
+        n = C.c_int64()
+        if isinstance(audio_bytes, int):
+            ptr, per = audio_bytes, int(bytes_per_stream)
+        else:
+            a = np.ascontiguousarray(np.frombuffer(audio_bytes, np.uint8) if isinstance(audio_bytes, (bytes, bytearray)) else audio_bytes)
+            a = a.view(np.uint8).reshape(self.n_streams, -1)
+            ptr, per = a.ctypes.data, a.shape[1]
+        _check(self._L.rp_batch_process_bytes(self._h, C.c_void_p(ptr), per, int(on_device), C.byref(dets), C.byref(n)), self._h)
+        return self._dets(dets, n)
+
+    def last_gate_stats(self):
+        """(tiles, passed) of the avg gate in the last process() — see rp_batch_last_gate_stats."""
+        t, p = C.c_int64(), C.c_int64()
+        _check(self._L.rp_batch_last_gate_stats(self._h, C.byref(t), C.byref(p)), self._h)
+        return int(t.value), int(p.value)
 
     def update_config(self, config: Config):
         _check(self._L.rp_batch_update_config(self._h, C.byref(config)), self._h)
@@ -387,6 +439,11 @@ def set_dtw_variant(v: int):
 
 def set_mfcc_variant(v: int):
     lib().rp_set_mfcc_variant(v)
+
+
+def set_avg_gate(mode: int):
+    """1 / -1 (default): avg gate first, templates only where it can pass; 0: dense scoring (parity taps, A/B)."""
+    lib().rp_set_avg_gate(mode)
 
 
 # ---------------------------------------------------------------- wakeword builder

@@ -1,5 +1,6 @@
 // extern "C" surface declared in include/rustpotter_b200.h.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -8,6 +9,7 @@
 #include <memory>
 #include <mutex>
 #include <optional>
+#include <thread>
 
 #include "audio_frontend.h"
 #include "detector_core.h"
@@ -27,7 +29,7 @@ struct HandleBase {
     uint32_t magic;
     std::string error;
 };
-int g_dtw_variant = 0;
+std::atomic<int> g_dtw_variant{0};   // debug / A-B knob, process-wide (see rp_set_dtw_variant)
 }  // namespace
 
 struct rp_handle {
@@ -42,12 +44,23 @@ struct rp_handle {
     mutable std::vector<float> partial_store;
 };
 
+// One shard = the contiguous stream range [begin, begin + count) on one device (streams shard with no collective).
+struct BatchShard {
+    std::unique_ptr<DetectorCore> core;
+    int64_t begin = 0, count = 0;
+    int device = 0;
+    std::vector<Emitted> emitted;
+};
 struct rp_batch {
     HandleBase base{kMagicBatch, {}};
-    std::unique_ptr<DetectorCore> core;
-    std::vector<Emitted> emitted;
+    std::vector<BatchShard> shards;
+    int64_t n_streams = 0;
+    rp_config cfg{};
     std::vector<rp_batch_detection> dets;
     std::vector<std::vector<float>> stores;
+    std::vector<float> timings = std::vector<float>(5, 0.f);
+    DetectorCore& first() { return *shards.front().core; }
+    const DetectorCore& first() const { return *shards.front().core; }
 };
 
 namespace {
@@ -117,6 +130,67 @@ const MfccTablesDev& tables_for(int device, int mfcc_size, cudaStream_t s) {
     return ref.dev;
 }
 
+}  // namespace
+
+namespace {
+std::atomic<int> g_avg_gate{-1};   // -1 default (gate on), 0 dense, 1 gate on: debug / A-B knob, process-wide
+
+// Runs f(shard) on every shard: inline for one shard, one host thread per device otherwise (each thread binds its device).
+template <typename F>
+void for_each_shard(rp_batch* b, F&& f) {
+    if (b->shards.size() == 1) {
+        f(b->shards.front());
+        return;
+    }
+    std::vector<std::thread> th;
+    std::vector<std::exception_ptr> errs(b->shards.size());
+    for (size_t i = 0; i < b->shards.size(); i++)
+        th.emplace_back([&, i] {
+            try {
+                f(b->shards[i]);
+            } catch (...) {
+                errs[i] = std::current_exception();
+            }
+        });
+    for (auto& t : th) t.join();
+    for (auto& e : errs)
+        if (e) std::rethrow_exception(e);
+}
+
+int batch_process(rp_batch* b, AudioIn in, const rp_batch_detection** dets, int64_t* n_dets) {
+    if (b->shards.size() > 1 && in.on_device)
+        throw Error(RP_ERR_INVALID, "a multi-device batch takes host audio (each device copies its own stream range)");
+    const size_t stream_bytes = in.bytes_per_stream();
+    const uint8_t* base = static_cast<const uint8_t*>(in.data);
+    const int gate = g_avg_gate.load();
+    for_each_shard(b, [&](BatchShard& sh) {
+        AudioIn mine = in;
+        mine.data = base + (size_t)sh.begin * stream_bytes;
+        sh.core->engine().set_dtw_variant(g_dtw_variant.load());
+        sh.core->engine().set_avg_gate(gate != 0);
+        sh.core->process(mine, nullptr, sh.emitted);
+    });
+    size_t total = 0;
+    for (auto& sh : b->shards) total += sh.emitted.size();
+    b->dets.resize(total);
+    b->stores.resize(total);
+    size_t i = 0;
+    for (auto& sh : b->shards)
+        for (auto& e : sh.emitted) {   // shards are contiguous and ascending: (stream, chunk) order is kept
+            b->dets[i].stream = sh.begin + e.stream;
+            b->dets[i].chunk = e.chunk;
+            sh.core->fill_detection(e.det, &b->dets[i].det, b->stores[i]);
+            i++;
+        }
+    std::fill(b->timings.begin(), b->timings.end(), 0.f);
+    for (auto& sh : b->shards) {   // devices run concurrently: the call's stage time is the slowest shard's
+        for (int k = 0; k < 4; k++) b->timings[k] = std::max(b->timings[k], sh.core->engine().timings_ms[k]);
+        b->timings[4] = std::max(b->timings[4], sh.core->host_ms);
+    }
+    if (dets) *dets = b->dets.data();
+    if (n_dets) *n_dets = (int64_t)b->dets.size();
+    return RP_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -278,24 +352,40 @@ void rp_reset(rp_handle* h) {
 uint64_t rp_windows_scored(const rp_handle* h) { return h ? h->core->windows_scored() : 0; }
 
 // ------------------------------------------------------------------ batch
-int rp_batch_create(const rp_config* cfg, int64_t n_streams, int device, rp_batch** out) {
+int rp_batch_create_multi(const rp_config* cfg, int64_t n_streams, const int* device_ids, int n_devices, rp_batch** out) {
     if (!cfg || !out) return RP_ERR_INVALID;
     *out = nullptr;
     return guarded((rp_batch*)nullptr, [&] {
+        if (!device_ids || n_devices < 1) throw Error(RP_ERR_INVALID, "at least one device id is needed");
+        if (n_streams < n_devices) throw Error(RP_ERR_INVALID, "fewer streams than devices");
         auto b = std::make_unique<rp_batch>();
-        b->core = std::make_unique<DetectorCore>(*cfg, n_streams, device);
-        b->core->enable_device_filters(*cfg);  // gain normaliser / band pass run as a GPU pre-stage
-        b->core->engine().set_dtw_variant(g_dtw_variant);
+        b->n_streams = n_streams;
+        b->cfg = *cfg;
+        for (int i = 0; i < n_devices; i++) {   // contiguous ranges [i*B/G, (i+1)*B/G)
+            BatchShard sh;
+            sh.begin = n_streams * i / n_devices;
+            sh.count = n_streams * (i + 1) / n_devices - sh.begin;
+            sh.device = device_ids[i];
+            sh.core = std::make_unique<DetectorCore>(*cfg, sh.count, sh.device);
+            sh.core->enable_device_filters(*cfg);  // gain normaliser / band pass run as a GPU pre-stage
+            sh.core->engine().set_dtw_variant(g_dtw_variant.load());
+            b->shards.push_back(std::move(sh));
+        }
         *out = b.release();
         return RP_OK;
     });
 }
+int rp_batch_create(const rp_config* cfg, int64_t n_streams, int device, rp_batch** out) {
+    return rp_batch_create_multi(cfg, n_streams, &device, 1, out);
+}
 void rp_batch_destroy(rp_batch* b) { delete b; }
+int rp_batch_n_devices(const rp_batch* b) { return b ? (int)b->shards.size() : 0; }
 
 int rp_batch_add_wakeword_from_buffer(rp_batch* b, const char* key, const uint8_t* buf, size_t len) {
     if (!b || !key || !buf) return RP_ERR_INVALID;
     return guarded(b, [&] {
-        b->core->add_wakeword(key, buf, len);
+        parse_rpw(buf, len);   // a malformed file fails before any shard is touched
+        for (auto& sh : b->shards) sh.core->add_wakeword(key, buf, len);
         return RP_OK;
     });
 }
@@ -303,74 +393,146 @@ int rp_batch_add_wakeword_from_file(rp_batch* b, const char* key, const char* pa
     if (!b || !key || !path) return RP_ERR_INVALID;
     return guarded(b, [&] {
         std::vector<uint8_t> f = read_file(path);
-        b->core->add_wakeword(key, f.data(), f.size());
+        parse_rpw(f.data(), f.size());
+        for (auto& sh : b->shards) sh.core->add_wakeword(key, f.data(), f.size());
         return RP_OK;
+    });
+}
+int rp_batch_remove_wakeword(rp_batch* b, const char* key) {
+    if (!b || !key) return RP_ERR_INVALID;
+    return guarded(b, [&] {
+        int removed = 0;
+        for (auto& sh : b->shards) removed = sh.core->remove_wakeword(key) ? 1 : 0;
+        return removed;
     });
 }
 int rp_batch_remove_wakewords(rp_batch* b) {
     if (!b) return RP_ERR_INVALID;
-    return guarded(b, [&] { return b->core->remove_wakewords() ? 1 : 0; });
+    return guarded(b, [&] {
+        int removed = 0;
+        for (auto& sh : b->shards) removed = sh.core->remove_wakewords() ? 1 : 0;
+        return removed;
+    });
 }
 int rp_batch_set_cuda_stream(rp_batch* b, void* s) {
     if (!b) return RP_ERR_INVALID;
     return guarded(b, [&] {
-        b->core->engine().set_cuda_stream(static_cast<cudaStream_t>(s));
+        if (b->shards.size() > 1 && s) throw Error(RP_ERR_INVALID, "a multi-device batch runs on its own per-device streams");
+        b->first().engine().set_cuda_stream(static_cast<cudaStream_t>(s));
         return RP_OK;
     });
 }
 int rp_batch_process(rp_batch* b, const float* audio, int64_t S, int on_device, const rp_batch_detection** dets, int64_t* n_dets) {
     if (!b || !audio) return RP_ERR_INVALID;
     return guarded(b, [&] {
-        b->core->engine().set_dtw_variant(g_dtw_variant);
-        b->core->process(audio, S, on_device != 0, nullptr, b->emitted);
-        b->dets.resize(b->emitted.size());
-        b->stores.resize(b->emitted.size());
-        for (size_t i = 0; i < b->emitted.size(); i++) {
-            b->dets[i].stream = b->emitted[i].stream;
-            b->dets[i].chunk = b->emitted[i].chunk;
-            b->core->fill_detection(b->emitted[i].det, &b->dets[i].det, b->stores[i]);
-        }
-        if (dets) *dets = b->dets.data();
-        if (n_dets) *n_dets = (int64_t)b->dets.size();
-        return RP_OK;
+        AudioIn in;
+        in.data = audio;
+        in.samples = S;
+        in.on_device = on_device != 0;
+        return batch_process(b, in, dets, n_dets);
+    });
+}
+int rp_batch_process_samples(rp_batch* b, const void* audio, int sample_format, int64_t samples_per_stream, int on_device,
+                             const rp_batch_detection** dets, int64_t* n_dets) {
+    if (!b || !audio) return RP_ERR_INVALID;
+    return guarded(b, [&] {
+        if (sample_format < RP_FMT_I8 || sample_format > RP_FMT_F32) throw Error(RP_ERR_INVALID, "unknown sample format");
+        const int64_t ch = (int64_t)b->cfg.channels;
+        if (samples_per_stream <= 0 || samples_per_stream % (kFrameSamples * ch) != 0)
+            throw Error(RP_ERR_INVALID, "samples_per_stream must be a positive multiple of 480 * channels");
+        AudioIn in;
+        in.data = audio;
+        in.fmt = sample_format;
+        in.channels = (int)ch;
+        in.big_endian = false;   // typed samples are in native (little-endian) byte order
+        in.samples = samples_per_stream / ch;
+        in.on_device = on_device != 0;
+        return batch_process(b, in, dets, n_dets);
+    });
+}
+int rp_batch_process_bytes(rp_batch* b, const uint8_t* bytes, int64_t bytes_per_stream, int on_device,
+                           const rp_batch_detection** dets, int64_t* n_dets) {
+    if (!b || !bytes) return RP_ERR_INVALID;
+    return guarded(b, [&] {
+        AudioIn in;
+        in.data = bytes;
+        in.fmt = (int)b->cfg.sample_format;
+        in.channels = (int)b->cfg.channels;
+        in.big_endian = b->cfg.endianness == RP_ENDIAN_BIG;
+        const int64_t frame_bytes = (int64_t)kFrameSamples * in.channels * (int64_t)in.bytes_per_sample();
+        if (bytes_per_stream <= 0 || bytes_per_stream % frame_bytes != 0)
+            throw Error(RP_ERR_INVALID, "bytes_per_stream must be a positive multiple of rp_get_bytes_per_frame()");
+        in.samples = bytes_per_stream / ((int64_t)in.channels * (int64_t)in.bytes_per_sample());
+        in.on_device = on_device != 0;
+        return batch_process(b, in, dets, n_dets);
     });
 }
 int rp_batch_update_config(rp_batch* b, const rp_config* cfg) {
     if (!b || !cfg) return RP_ERR_INVALID;
     return guarded(b, [&] {
-        b->core->update_detector_config(*cfg);   // update_config = detector config, then filters config (detector.rs:259-262)
-        b->core->update_filters_config(*cfg);
+        validate_detector_config(*cfg);
+        for (auto& sh : b->shards) {
+            sh.core->update_detector_config(*cfg);   // update_config = detector config, then filters config (detector.rs:259-262)
+            sh.core->update_filters_config(*cfg);
+        }
         return RP_OK;
     });
 }
 void rp_batch_reset(rp_batch* b) {
-    if (b) b->core->reset();
+    if (b)
+        for (auto& sh : b->shards) sh.core->reset();
 }
-uint64_t rp_batch_windows_scored(const rp_batch* b) { return b ? b->core->windows_scored() : 0; }
-int64_t rp_batch_n_streams(const rp_batch* b) { return b ? b->core->engine().n_streams() : 0; }
-int rp_batch_max_mfcc_frames(const rp_batch* b) { return b ? b->core->wakewords().max_frames : 0; }
+uint64_t rp_batch_windows_scored(const rp_batch* b) {
+    uint64_t t = 0;
+    if (b)
+        for (auto& sh : b->shards) t += sh.core->windows_scored();
+    return t;
+}
+int64_t rp_batch_n_streams(const rp_batch* b) { return b ? b->n_streams : 0; }
+int rp_batch_max_mfcc_frames(const rp_batch* b) { return b ? b->first().wakewords().max_frames : 0; }
 int rp_batch_last_timings(const rp_batch* b, float* ms, int cap) {
     if (!b || !ms) return 0;
     int n = 0;
-    for (; n < 4 && n < cap; n++) ms[n] = b->core->engine().timings_ms[n];
-    if (n < cap) ms[n++] = b->core->host_ms;
+    for (; n < 5 && n < cap; n++) ms[n] = b->timings[(size_t)n];
     return n;
 }
-int rp_batch_last_launches(const rp_batch* b) { return b ? b->core->engine().launches : 0; }
+int rp_batch_last_launches(const rp_batch* b) {
+    int n = 0;
+    if (b)
+        for (auto& sh : b->shards) n += sh.core->engine().launches;
+    return n;
+}
+int rp_batch_last_gate_stats(const rp_batch* b, int64_t* tiles, int64_t* passed) {
+    if (!b) return RP_ERR_INVALID;
+    return guarded(const_cast<rp_batch*>(b), [&] {
+        int64_t t = 0, p = 0;
+        for (auto& sh : b->shards) {
+            int64_t a = 0, c = 0;
+            sh.core->engine().last_gate_stats(&a, &c);
+            t += a;
+            p += c;
+        }
+        if (tiles) *tiles = t;
+        if (passed) *passed = p;
+        return RP_OK;
+    });
+}
 int64_t rp_batch_copy_last_scores(const rp_batch* b, float* out, int64_t cap, int32_t* n_new, int32_t* n_slots) {
     if (!b || !out) return RP_ERR_INVALID;
     return guarded(const_cast<rp_batch*>(b), [&]() -> int {
-        const Engine& e = b->core->engine();
-        const int64_t n = e.n_streams() * (int64_t)e.last_n_new() * e.n_slots();
-        if (n_new) *n_new = e.last_n_new();
-        if (n_slots) *n_slots = e.n_slots();
+        const Engine& e0 = b->first().engine();
+        const int64_t per_stream = (int64_t)e0.last_n_new() * e0.n_slots();
+        const int64_t n = b->n_streams * per_stream;
+        if (n_new) *n_new = e0.last_n_new();
+        if (n_slots) *n_slots = e0.n_slots();
         if (n > cap) throw Error(RP_ERR_INVALID, "output buffer too small");
-        if (n > 0) {
-            cuda_check(cudaSetDevice(e.device()), "cudaSetDevice");
-            cuda_check(cudaMemcpy(out, e.last_scores_dev(), (size_t)n * sizeof(float), cudaMemcpyDeviceToHost), "D2H scores");
-        }
+        for (auto& sh : b->shards) sh.core->engine().copy_last_scores(out + sh.begin * per_stream);
         return (int)std::min<int64_t>(n, 0x7fffffff);
     });
+}
+int rp_set_avg_gate(int mode) {
+    g_avg_gate.store(mode < 0 ? -1 : (mode ? 1 : 0));
+    return RP_OK;
 }
 
 // ------------------------------------------------------------------ wakeword builder
@@ -493,7 +655,7 @@ int rp_dtw_scores(const float* tmpl_dev, const int64_t* tmpl_off_dev, const int3
         a.score_ref = score_ref;
         a.cmn = cmn;
         a.out = out_dev;
-        if (g_dtw_variant != 1 && dtw_pairs_stream_supported(a))
+        if (g_dtw_variant.load() != 1 && dtw_pairs_stream_supported(a))
             cuda_check(launch_dtw_pairs_stream(a, static_cast<cudaStream_t>(cuda_stream)), "dtw stream kernel");
         else
             cuda_check(launch_dtw_pairs_generic(a, static_cast<cudaStream_t>(cuda_stream)), "dtw kernel");
@@ -506,9 +668,9 @@ int rp_set_dtw_variant(int v) {
     // 4 tuned with the two-windows-per-thread pipeline kernel, 5 tuned with the round-1 two-rows-per-step
     // streaming kernel, 6 tuned with the v3 streaming kernel, 7 tuned with the pipeline kernel reading its templates from
     // shared instead of constant memory (alternatives kept for A/B measurements)
-    g_dtw_variant = v >= 3 ? 2 : v;
+    g_dtw_variant.store(v >= 3 ? 2 : v);
     set_dtw_stream_rows(v == 3 ? 1 : (v == 5 ? 2 : (v == 6 ? 3 : 0)));
-    set_dtw_window_kernel(v == 4 ? 2 : (v == 7 ? 3 : 0));
+    set_dtw_window_kernel(v == 7 ? 3 : 0);
     return RP_OK;
 }
 

@@ -11,9 +11,9 @@ DetectorCore::DetectorCore(const rp_config& cfg, int64_t n_streams, int device) 
     if (cfg.sample_rate != (uint32_t)kSampleRate)
         throw Error(RP_ERR_UNSUPPORTED,
                     "sample_rate != 16000 needs the reference's rubato resampler, which is outside this path");
-    if (cfg.sample_format > RP_FMT_F32 || cfg.channels == 0 || cfg.endianness > RP_ENDIAN_NATIVE || cfg.score_mode > RP_SCORE_P95 ||
-        cfg.vad_mode > RP_VAD_HARD)
+    if (cfg.sample_format > RP_FMT_F32 || cfg.channels == 0 || cfg.endianness > RP_ENDIAN_NATIVE)
         throw Error(RP_ERR_INVALID, "invalid configuration value");
+    validate_detector_config(cfg);
     engine_ = std::make_unique<Engine>(device, n_streams);
     states_.resize((size_t)n_streams);
     params_.min_scores = cfg.min_scores;
@@ -42,23 +42,35 @@ bool DetectorCore::remove_wakewords() {
     return true;
 }
 
+std::shared_ptr<const WakewordNames> make_wakeword_names(const WakewordRefData& r) {
+    auto n = std::make_shared<WakewordNames>();
+    n->name = r.name;
+    for (auto& t : r.samples_features) n->templates.push_back(t.first);
+    for (auto& t : n->templates) n->template_cstrs.push_back(t.c_str());
+    return n;
+}
+
 void DetectorCore::on_wakeword_change() {
     ws_.rebuild(cfg_);
     params_.max_frames = ws_.max_frames;
     engine_->configure(ws_, cfg_);
     names_.clear();
-    for (auto& r : ws_.refs) {
-        std::vector<const char*> n;
-        for (auto& t : r.samples_features) n.push_back(t.first.c_str());
-        names_.push_back(std::move(n));
-    }
+    for (auto& r : ws_.refs) names_.push_back(make_wakeword_names(r));
     // Deviation: the reference would keep scoring a window longer than the new
     // max_mfcc_frames after a removal; here the window is clamped to the new length.
     for (auto& s : states_) s.clamp_window(params_.max_frames);
     if (device_filters_) engine_->set_gain_reference(ws_.target_rms_level, ws_.max_frames / 3);  // detector.rs:336-338
 }
 
+// The enum-valued fields of DetectorConfig (config.rs:86-97,134-139): one check for construction and updates.
+void validate_detector_config(const rp_config& cfg) {
+    if (cfg.score_mode > RP_SCORE_P95) throw Error(RP_ERR_INVALID, "invalid score_mode");
+    if (cfg.vad_mode < RP_VAD_NONE || cfg.vad_mode > RP_VAD_HARD) throw Error(RP_ERR_INVALID, "invalid vad_mode");
+    if (cfg.band_size > 0xffffu) throw Error(RP_ERR_INVALID, "band_size does not fit the reference's u16");
+}
+
 void DetectorCore::update_detector_config(const rp_config& cfg) {
+    validate_detector_config(cfg);   // nothing is changed when a value is out of range
     cfg_.avg_threshold = cfg.avg_threshold;
     cfg_.threshold = cfg.threshold;
     cfg_.min_scores = cfg.min_scores;
@@ -98,15 +110,17 @@ uint64_t DetectorCore::windows_scored() const {
     return t;
 }
 
-void DetectorCore::process(const float* audio, int64_t S, bool on_device, const float* gains, std::vector<Emitted>& out) {
+void DetectorCore::process(const AudioIn& in, const float* gains, std::vector<Emitted>& out) {
     out.clear();
     if (ws_.empty()) return;  // detector.rs:348-350: audio is dropped, extractor untouched
-    if (S <= 0 || S % kFrameSamples != 0) throw Error(RP_ERR_INVALID, "samples_per_stream must be a positive multiple of 480");
+    const int64_t S = in.samples;
+    if (S <= 0 || S % kFrameSamples != 0) throw Error(RP_ERR_INVALID, "samples_per_stream must be a positive multiple of 480 per channel");
+    if (!in.data || in.channels < 1 || in.fmt < RP_FMT_I8 || in.fmt > RP_FMT_F32) throw Error(RP_ERR_INVALID, "bad audio description");
     const bool vad = params_.vad_mode >= 0;
     // leading hops of this call that no stream can turn into a scored window (e.g. a freshly reset batch)
     int64_t skip = S / kHopSamples;
     for (const StreamState& st : states_) skip = std::min(skip, st.hops_until_scorable(params_));
-    engine_->process(audio, S, on_device, vad, (int)std::max<int64_t>(skip, 0), hits_, vad ? &vad_ : nullptr);
+    engine_->process(in, vad, (int)std::max<int64_t>(skip, 0), hits_, vad ? &vad_ : nullptr);
 
     const auto t0 = std::chrono::steady_clock::now();
     const int64_t n_chunks = S / kFrameSamples;
@@ -148,6 +162,7 @@ void DetectorCore::process(const float* audio, int64_t S, bool on_device, const 
                     hit.score = r.score;
                     hit.scores = r.scores;
                     hit.n_scores = ws_.metas[(size_t)r.wakeword].n_templates;
+                    hit.names = names_[(size_t)r.wakeword];
                     hptr = &hit;
                 }
                 PartialDetection det;
@@ -165,15 +180,16 @@ void DetectorCore::process(const float* audio, int64_t S, bool on_device, const 
 
 void DetectorCore::fill_detection(const PartialDetection& d, rp_detection* out, std::vector<float>& score_store) const {
     std::memset(out, 0, sizeof(*out));
-    const WakewordRefData& r = ws_.refs[(size_t)d.wakeword];
-    std::snprintf(out->name, RP_NAME_MAX, "%s", r.name.c_str());
+    if (!d.names) throw Error(RP_ERR_INVALID, "detection without a wakeword name snapshot");
+    std::snprintf(out->name, RP_NAME_MAX, "%s", d.names->name.c_str());
     out->avg_score = d.avg_score;
     out->score = d.score;
     out->counter = d.counter;
     out->gain = d.gain;
     score_store = d.scores;
-    out->n_scores = (uint32_t)score_store.size();
-    out->score_names = names_[(size_t)d.wakeword].data();
+    // (a replaced wakeword may have fewer templates than the detection has scores: the snapshot is the detection's own)
+    out->n_scores = (uint32_t)std::min(score_store.size(), d.names->template_cstrs.size());
+    out->score_names = d.names->template_cstrs.data();
     out->score_values = score_store.data();
 }
 

@@ -17,6 +17,9 @@ struct Emitted {
     PartialDetection det;
 };
 
+void validate_detector_config(const rp_config& cfg);  // throws RP_ERR_INVALID
+std::shared_ptr<const WakewordNames> make_wakeword_names(const WakewordRefData& r);
+
 class DetectorCore {
   public:
     DetectorCore(const rp_config& cfg, int64_t n_streams, int device);
@@ -30,10 +33,17 @@ class DetectorCore {
     void enable_device_filters(const rp_config& cfg);   // batched front-end only
     void reset();                                       // :290-302
 
-    // n_chunks * 480 samples per stream; gains: per-chunk gain stamped on detections (nullptr = 1.0)
-    void process(const float* audio, int64_t samples_per_stream, bool on_device, const float* gains, std::vector<Emitted>& out);
+    // in.samples = n_chunks * 480 mono samples per stream; gains: per-chunk gain stamped on detections (nullptr = 1.0)
+    void process(const AudioIn& in, const float* gains, std::vector<Emitted>& out);
+    void process(const float* audio, int64_t samples_per_stream, bool on_device, const float* gains, std::vector<Emitted>& out) {
+        AudioIn in;
+        in.data = audio;
+        in.samples = samples_per_stream;
+        in.on_device = on_device;
+        process(in, gains, out);
+    }
 
-    // Fills an rp_detection whose pointers refer to `names_` and to `score_store` (caller-owned).
+    // Fills an rp_detection whose pointers refer to the detection's own name snapshot and to `score_store` (caller-owned).
     void fill_detection(const PartialDetection& d, rp_detection* out, std::vector<float>& score_store) const;
     const std::optional<PartialDetection>& partial(int64_t stream) const { return states_[stream].partial(); }
     uint64_t windows_scored() const;
@@ -51,7 +61,7 @@ class DetectorCore {
     DetectorParams params_;
     std::unique_ptr<Engine> engine_;
     std::vector<StreamState> states_;
-    std::vector<std::vector<const char*>> names_;  // per wakeword: template names (for rp_detection)
+    std::vector<std::shared_ptr<const WakewordNames>> names_;  // per wakeword; a fresh snapshot after every change
     std::vector<HitRecord> hits_;
     std::vector<float> vad_;
     bool device_filters_ = false;

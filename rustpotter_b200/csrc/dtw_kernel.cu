@@ -148,7 +148,9 @@ __global__ void __launch_bounds__(kGenericWarps * 32) dtw_windows_generic_kernel
         if (j < a.first_window) continue;  // warp-uniform
         PairView pv;
         pv.m = a.slot_len[s];
-        pv.n = pv.m;  // cut_and_normalize_frame keeps the first m frames of the window (wakeword_comp.rs:22-27)
+        // cut_and_normalize_frame keeps the first m frames of the window (wakeword_comp.rs:22-27); the window holds
+        // max_mfcc_frames rows, so an avg_features matrix longer than every template meets n < m
+        pv.n = a.window_len > 0 && a.window_len < pv.m ? a.window_len : pv.m;
         pv.a = a.tmpl + a.slot_off[s];
         pv.b = a.frames + ((b * a.frame_rows) + a.first_window_row + j) * (int64_t)a.d;
         const float sc = dtw_pair_faithful(pv, a.d, a.band, a.score_ref, 1, sm, a.max_len, a.max_len, lane);

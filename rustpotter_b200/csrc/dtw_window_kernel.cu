@@ -1,4 +1,4 @@
-// K2p — tuned window scorer for the detector pipeline (mfcc_size = 16), sm_100a.
+// K2p — tuned window scorer for the detector pipeline (mfcc_size <= 16, band_size 1..20), sm_100a.
 //
 // Same arithmetic contract as the generic kernel in dtw_kernel.cu (reference
 // src/wakewords/comp/wakeword_comp.rs:22-37 + src/mfcc/{normalizer,comparator,dtw}.rs), restructured
@@ -24,9 +24,21 @@
 // The returned cell is D[m-1][n] (dtw.rs:101), i.e. band offset W+1 after row m-1; row m is never
 // computed. Left-border cells (c < 1) stay +inf by induction once row 1 is special-cased; right-
 // border cells (c > m) hold garbage that no valid cell ever reads.
+//
+// Shapes. mfcc_size < 16 is zero-padded to 16 while the frame tile is staged (zero columns change neither dot
+// products nor norms; the unit templates arrive padded). The band is a template parameter W; band_size 5 (the
+// reference's default, config.rs:193-208) runs the exact W = 5 instance, any other band_size <= 20 runs the next
+// larger W in {5, 8, 12, 20} with the cells outside [r-band, r+band-1] forced to +inf after every row (MASK).
+//
+// Avg gate (wakeword_comp.rs:85-94: a wakeword whose avg_features score is below avg_threshold is not scored against
+// its templates). The engine launches the avg slots first (gate == 1: every CTA ORs "score >= avg_threshold" over its
+// 128 windows into tile_pass[stream][window block][wakeword]) and then the template slots (gate == 2: a CTA whose
+// tile has no passing window returns at once). A tile with one passing window scores all its windows: a superset of
+// what the reference computes, so detections are identical; K3 never reads the scores that were skipped.
 #include <cfloat>
 #include <cmath>
 
+#include <atomic>
 #include <mutex>
 
 #include "kernels.h"
@@ -104,9 +116,21 @@ __device__ __forceinline__ Row16 ldc_row(int f4_index) {
     return r;
 }
 
-template <int W, bool CT>
-__global__ void __launch_bounds__(kThreads, 5) dtw_windows_d16_kernel(DtwWindowsArgs a, const float* __restrict__ tmpl_unit,
-                                                                   int x_rows, int j_blocks) {
+struct WindowLaunch {              // what one launch covers (device pointers)
+    const int32_t* slots;          // [n_slots] slot ids of this launch, or nullptr: slot i = i
+    int n_slots;
+    const int64_t* unit_off;       // [a.n_slots] offset of the slot's unit template in tmpl_unit (floats, rows of 16)
+    int gate;                      // 0: no gate; 1: avg slots, write tile_pass; 2: template slots, read tile_pass
+    const int32_t* slot_ww;        // [a.n_slots] wakeword of a slot
+    const WakewordMeta* metas;     // [n_wakewords]
+    int n_wakewords;
+    unsigned char* tile_pass;      // [n_streams][j_blocks][n_wakewords]
+    int band;                      // band_size (MASK instances)
+};
+
+template <int W, bool CT, bool MASK>
+__global__ void __launch_bounds__(kThreads, (W <= 5 ? 5 : W <= 8 ? 3 : 2))
+dtw_windows_d16_kernel(DtwWindowsArgs a, WindowLaunch L, const float* __restrict__ tmpl_unit, int x_rows, int j_blocks) {
     constexpr int NB = 2 * W;  // band cells per row
     extern __shared__ __align__(16) float sm[];
     float* Xs = sm;                              // [x_rows][kXS] frame tile (raw frames)
@@ -120,27 +144,40 @@ __global__ void __launch_bounds__(kThreads, 5) dtw_windows_d16_kernel(DtwWindows
 
     const int tid = threadIdx.x;
     const int64_t cta = blockIdx.x;
-    const int s = (int)(cta % a.n_slots);
-    const int64_t rest = cta / a.n_slots;
+    const int si = (int)(cta % L.n_slots);
+    const int s = L.slots ? L.slots[si] : si;
+    const int64_t rest = cta / L.n_slots;
     const int jb = (int)(rest % j_blocks);
     const int64_t b = rest / j_blocks;
+    unsigned char* const tile = L.gate ? L.tile_pass + ((b * j_blocks + jb) * L.n_wakewords + L.slot_ww[s]) : nullptr;
+    if (L.gate == 2 && *tile == 0) return;   // no window of this tile passed the wakeword's avg gate (uniform over the CTA)
     const int j0 = a.first_window + jb * kNW;
     const int m = a.slot_len[s];
-    const int c_row0 = CT ? (int)(a.slot_off[s] >> 2) : 0;   // float4 index of the slot's first row in c_tmpl_unit
+    const int c_row0 = CT ? (int)(L.unit_off[s] >> 2) : 0;   // float4 index of the slot's first row in c_tmpl_unit
+    // MASK: band offsets i (column c = r - W + i) inside the reference's band [r-band, r+band-1]
+    const unsigned long long band_mask = MASK ? (((1ull << (2 * L.band)) - 1ull) << (W - L.band)) : ~0ull;
 
     // ---- stage the frame tile and the template in shared memory
     {
         const int64_t row0 = (int64_t)a.first_window_row + j0;
         const float* src = a.frames + (b * a.frame_rows + row0) * kD;
         const int64_t avail = a.frame_rows - row0;  // rows of this stream from row0 on
-        for (int i = tid; i < x_rows * 4; i += kThreads) {
-            const int u = i >> 2, q = i & 3;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (u < avail) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)u * kD) + q);
-            *reinterpret_cast<float4*>(Xs + u * kXS + 4 * q) = v;
+        if (a.d == kD) {
+            for (int i = tid; i < x_rows * 4; i += kThreads) {
+                const int u = i >> 2, q = i & 3;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (u < avail) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)u * kD) + q);
+                *reinterpret_cast<float4*>(Xs + u * kXS + 4 * q) = v;
+            }
+        } else {   // mfcc_size < 16: rows of d floats, zero-padded to 16
+            const float* srcd = a.frames + (b * a.frame_rows + row0) * a.d;
+            for (int i = tid; i < x_rows * kD; i += kThreads) {
+                const int u = i >> 4, q = i & 15;
+                Xs[u * kXS + q] = (u < avail && q < a.d) ? __ldg(srcd + (size_t)u * a.d + q) : 0.f;
+            }
         }
         if (!CT) {
-            const float4* ts = reinterpret_cast<const float4*>(tmpl_unit + a.slot_off[s]);
+            const float4* ts = reinterpret_cast<const float4*>(tmpl_unit + L.unit_off[s]);
             for (int i = tid; i < m * 4; i += kThreads) reinterpret_cast<float4*>(Ts)[i] = __ldg(ts + i);
         }
     }
@@ -248,16 +285,18 @@ __global__ void __launch_bounds__(kThreads, 5) dtw_windows_d16_kernel(DtwWindows
                     inv[(k + W) % NB] = n2 > 0.f ? rsqrtf(n2) : 0.f;  // column r+W-1 = (k+1)+W-1 mod NB
                     G[t + NB - 1] = hsum(g);
                     A = -hsum(aa);                                     // a^_r . mu  (nmu is negated)
-                } else if (tid >= kNW && tid - kNW < NB - 1) {
+                } else if (tid >= kNW) {
                     // helper warp: the NB-1 lowest frames of this row's shared range
-                    const int e = tid - kNW;
-                    const int u = r - W - 1 + e;
-                    float g = 0.f;
-                    if (u >= 0) {
-                        const Row16 x = lds_row(Xs + u * kXS);
-                        g = dot16(ar, x);
+#pragma unroll
+                    for (int e = tid - kNW; e < NB - 1; e += 32) {
+                        const int u = r - W - 1 + e;
+                        float g = 0.f;
+                        if (u >= 0) {
+                            const Row16 x = lds_row(Xs + u * kXS);
+                            g = dot16(ar, x);
+                        }
+                        G[e] = g;
                     }
-                    G[e] = g;
                 }
                 __syncthreads();
                 if (dp) {
@@ -267,7 +306,8 @@ __global__ void __launch_bounds__(kThreads, 5) dtw_windows_d16_kernel(DtwWindows
                         for (int i = W; i < NB; i++) {
                             const float sim = (G[t + i] - A) * inv[(k + i + 1 + NB - W) % NB];
                             const float best = min3(i + 1 < NB ? D[i + 1] : INFINITY, D[i], D[i - 1]);
-                            D[i] = (1.f - sim) + best;
+                            const float v = (1.f - sim) + best;
+                            D[i] = (!MASK || ((band_mask >> i) & 1ull)) ? v : INFINITY;
                         }
                         D[W - 1] = INFINITY;
                     } else {
@@ -276,245 +316,37 @@ __global__ void __launch_bounds__(kThreads, 5) dtw_windows_d16_kernel(DtwWindows
                             // column c = r - W + i  ->  inv slot c % NB = (k + 1 - W + i) mod NB
                             const float sim = (G[t + i] - A) * inv[(k + i + 1 + NB - W) % NB];
                             const float best = min3(i + 1 < NB ? D[i + 1] : INFINITY, D[i], i > 0 ? D[i - 1] : INFINITY);
-                            D[i] = (1.f - sim) + best;
+                            const float v = (1.f - sim) + best;
+                            D[i] = (!MASK || ((band_mask >> i) & 1ull)) ? v : INFINITY;
                         }
                     }
                 }
             }
         }
     }
+    bool pass = false;
     if (live) {
         // D[m-1][m] = band offset W+1 of row m-1 (dtw.rs:101); m == 1 has no such cell -> +inf
         const float cost = m >= 2 ? D[W + 1] : INFINITY;
         const float normalized = __fdiv_rn(cost, (float)(2 * m));
         const float score = __fdiv_rn(1.f, 1.f + expf(__fdiv_rn(normalized - a.score_ref, a.score_ref)));
         a.scores[(b * a.n_new + (j0 + tid)) * a.n_slots + s] = score;
-    }
-}
-
-// =============================================================================================
-// Two windows per thread. Thread t of 64 scores windows 2t and 2t+1 of the CTA's 128: the frame that
-// enters window 2t+1's band at row r is the one that enters window 2t's band at row r+1, so ONE frame
-// is read from shared memory per thread-row for two windows (it is kept in registers for the next
-// row), each thread contributes two shared dots G_r[u] per row, and the 2 x 10 values the two DP rows
-// need are 11 consecutive floats read as aligned 64-bit loads. Shared-memory wavefronts per window-row
-// drop from ~31 to ~18 and each thread carries two independent DP chains. MEASURED (r01): 30.7 ms vs
-// 23.6 ms per config-2 step for the one-window kernel — at 142 registers only 8 DP warps fit per SM and
-// the kernel turns latency-bound, so it is NOT the default; kept selectable (rp_set_dtw_variant(4)).
-constexpr int kNT2 = kNW / 2;            // DP threads
-constexpr int kThreads2 = kNT2 + 32;     // + helper warp
-
-template <int W>
-__global__ void __launch_bounds__(kThreads2) dtw_windows_d16x2_kernel(DtwWindowsArgs a, const float* __restrict__ tmpl_unit,
-                                                                     int x_rows, int j_blocks) {
-    constexpr int NB = 2 * W;
-    extern __shared__ __align__(16) float sm[];
-    float* Xs = sm;
-    float* Ts = Xs + (size_t)x_rows * kXS;
-    float* Gs = Ts + (size_t)a.max_len * kD;
-    constexpr int GS = kNW + NB + 2;             // even, so both buffers stay 8-byte aligned
-    float* Os = Gs + 2 * GS;
-    constexpr int NSEG = kThreads2 / 16;         // 6 prefix segments x 16 coefficients
-    const int p_rows = kNW + a.max_len + 1;
-    const int SEG = (p_rows + NSEG - 1) / NSEG;
-    float* Ps = Os + (NSEG + 2) * kD;
-
-    const int tid = threadIdx.x;
-    const int64_t cta = blockIdx.x;
-    const int s = (int)(cta % a.n_slots);
-    const int64_t rest = cta / a.n_slots;
-    const int jb = (int)(rest % j_blocks);
-    const int64_t b = rest / j_blocks;
-    const int j0 = a.first_window + jb * kNW;
-    const int m = a.slot_len[s];
-
-    {
-        const int64_t row0 = (int64_t)a.first_window_row + j0;
-        const float* src = a.frames + (b * a.frame_rows + row0) * kD;
-        const int64_t avail = a.frame_rows - row0;
-        for (int i = tid; i < x_rows * 4; i += kThreads2) {
-            const int u = i >> 2, q = i & 3;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (u < avail) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)u * kD) + q);
-            *reinterpret_cast<float4*>(Xs + u * kXS + 4 * q) = v;
-        }
-        const float4* ts = reinterpret_cast<const float4*>(tmpl_unit + a.slot_off[s]);
-        for (int i = tid; i < m * 4; i += kThreads2) reinterpret_cast<float4*>(Ts)[i] = __ldg(ts + i);
-    }
-    __syncthreads();
-
-    // ---- exclusive row prefix sums (per segment) for the window means
-    {
-        const int seg = tid >> 4, dd = tid & 15;
-        float run = 0.f;
-        for (int i = 0; i < SEG; i++) {
-            const int u = seg * SEG + i;
-            if (u < p_rows) {
-                Ps[u * kXS + dd] = run;
-                if (u < x_rows) run += Xs[u * kXS + dd];
-            }
-        }
-        Os[(seg + 1) * kD + dd] = run;
-        __syncthreads();
-        if (tid < kD) {
-            float acc = 0.f;
-            Os[tid] = 0.f;
-            for (int g = 1; g <= NSEG; g++) {
-                acc += Os[g * kD + tid];
-                Os[g * kD + tid] = acc;
-            }
-        }
-        __syncthreads();
-    }
-
-    const bool dp = tid < kNT2;
-    const int t = dp ? tid : 0;
-    const int wa = 2 * t;                       // window A; window B = wa + 1
-    auto window_mean = [&](int w0, f2 (&nmu)[8]) {   // NEGATED mean of rows [w0, w0+m)
-        const int u0 = w0, u1 = w0 + m;
-        const Row16 p0 = lds_row(Ps + u0 * kXS), p1 = lds_row(Ps + u1 * kXS);
-        const Row16 o0 = lds_row(Os + (u0 / SEG) * kD), o1 = lds_row(Os + (u1 / SEG) * kD);
-        const float fm = (float)m;
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            float a0, a1, b0, b1, c0, c1, d0, d1;
-            asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(p1.p[q]));
-            asm("mov.b64 {%0, %1}, %2;" : "=f"(b0), "=f"(b1) : "l"(p0.p[q]));
-            asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(o1.p[q]));
-            asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(o0.p[q]));
-            nmu[q] = pk(-__fdiv_rn((a0 - b0) + (c0 - d0), fm), -__fdiv_rn((a1 - b1) + (c1 - d1), fm));
-        }
-    };
-    f2 nmuA[8], nmuB[8];
-    window_mean(wa, nmuA);
-    window_mean(wa + 1, nmuB);
-
-    auto inv_norm = [&](const Row16& x, const f2 (&nmu)[8]) -> float {  // 1/|x - mu|, 0 for the zero vector
-        f2 nn = 0ull;
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const f2 y = add2(x.p[q], nmu[q]);
-            nn = fma2(y, y, nn);
-        }
-        const float n2 = hsum(nn);
-        return n2 > 0.f ? rsqrtf(n2) : 0.f;
-    };
-
-    float DA[NB], DB[NB], invA[NB], invB[NB];
-#pragma unroll
-    for (int i = 0; i < NB; i++) {
-        DA[i] = INFINITY;
-        DB[i] = INFINITY;
-        invA[i] = 0.f;
-        invB[i] = 0.f;
-    }
-    DA[W] = 0.f;
-    DB[W] = 0.f;
-    // columns 1 .. W-1 of both windows (column c of window w is frame w + c - 1)
-    if (dp) {
-#pragma unroll
-        for (int c = 1; c < W; c++) {
-            invA[c % NB] = inv_norm(lds_row(Xs + (wa + c - 1) * kXS), nmuA);
-            invB[c % NB] = inv_norm(lds_row(Xs + (wa + c) * kXS), nmuB);
+        if (L.gate == 1) {   // the comparison K3 makes (score_logic.h judge_window): avg_score < avg_threshold => skip
+            const float thr = L.metas[L.slot_ww[s]].avg_threshold;
+            pass = thr == 0.f || !(score < thr);
         }
     }
-    // frame entering window A's band at row 1 (column W): u = wa + W - 1; kept in registers across rows
-    Row16 xprev = lds_row(Xs + (wa + W - 1) * kXS);
-
-    const int last_row = m - 1;
-    for (int r0 = 0; r0 < last_row; r0 += NB) {
-#pragma unroll
-        for (int k = 0; k < NB; k++) {
-            const int r = r0 + k + 1;
-            if (r <= last_row) {
-                float* G = Gs + (r & 1) * GS;
-                const Row16 ar = lds_row(Ts + (r - 1) * kD);
-                float AA = 0.f, AB = 0.f;
-                if (dp) {
-                    // window A's new column r+W-1 is frame uA = wa + r + W - 2 (= xprev); window B's is uA + 1
-                    const int uA = wa + r + W - 2;
-                    const Row16 xnew = lds_row(Xs + (uA + 1) * kXS);
-                    f2 nnA = 0ull, nnB = 0ull, gA = 0ull, gB = 0ull, aA = 0ull, aB = 0ull;
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        const f2 yA = add2(xprev.p[q], nmuA[q]);
-                        const f2 yB = add2(xnew.p[q], nmuB[q]);
-                        nnA = fma2(yA, yA, nnA);
-                        nnB = fma2(yB, yB, nnB);
-                        gA = fma2(ar.p[q], xprev.p[q], gA);
-                        gB = fma2(ar.p[q], xnew.p[q], gB);
-                        aA = fma2(ar.p[q], nmuA[q], aA);
-                        aB = fma2(ar.p[q], nmuB[q], aB);
-                    }
-                    const float n2A = hsum(nnA), n2B = hsum(nnB);
-                    invA[(k + W) % NB] = n2A > 0.f ? rsqrtf(n2A) : 0.f;
-                    invB[(k + W) % NB] = n2B > 0.f ? rsqrtf(n2B) : 0.f;
-                    G[wa + NB - 1] = hsum(gA);      // index u - (r - W - 1)
-                    G[wa + NB] = hsum(gB);
-                    AA = -hsum(aA);
-                    AB = -hsum(aB);
-                    xprev = xnew;
-                } else if (tid - kNT2 < NB - 1) {
-                    const int e = tid - kNT2;
-                    const int u = r - W - 1 + e;
-                    float g = 0.f;
-                    if (u >= 0) g = dot16(ar, lds_row(Xs + u * kXS));
-                    G[e] = g;
-                }
-                __syncthreads();
-                if (dp) {
-                    // G[wa .. wa+NB]: NB+1 consecutive floats from an even index -> 64-bit loads
-                    float gv[NB + 2];
-#pragma unroll
-                    for (int i = 0; i < NB + 2; i += 2) {
-                        const float2 v = *reinterpret_cast<const float2*>(G + wa + i);
-                        gv[i] = v.x;
-                        gv[i + 1] = v.y;
-                    }
-                    if (r == 1) {
-#pragma unroll
-                        for (int i = W; i < NB; i++) {
-                            const float iv_a = invA[(k + i + 1 + NB - W) % NB], iv_b = invB[(k + i + 1 + NB - W) % NB];
-                            const float bestA = min3(i + 1 < NB ? DA[i + 1] : INFINITY, DA[i], DA[i - 1]);
-                            const float bestB = min3(i + 1 < NB ? DB[i + 1] : INFINITY, DB[i], DB[i - 1]);
-                            DA[i] = (1.f - (gv[i] - AA) * iv_a) + bestA;
-                            DB[i] = (1.f - (gv[i + 1] - AB) * iv_b) + bestB;
-                        }
-                        DA[W - 1] = INFINITY;
-                        DB[W - 1] = INFINITY;
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < NB; i++) {
-                            const float iv_a = invA[(k + i + 1 + NB - W) % NB], iv_b = invB[(k + i + 1 + NB - W) % NB];
-                            const float bestA = min3(i + 1 < NB ? DA[i + 1] : INFINITY, DA[i], i > 0 ? DA[i - 1] : INFINITY);
-                            const float bestB = min3(i + 1 < NB ? DB[i + 1] : INFINITY, DB[i], i > 0 ? DB[i - 1] : INFINITY);
-                            DA[i] = (1.f - (gv[i] - AA) * iv_a) + bestA;
-                            DB[i] = (1.f - (gv[i + 1] - AB) * iv_b) + bestB;
-                        }
-                    }
-                }
-            }
-        }
-    }
-    if (dp) {
-#pragma unroll
-        for (int wsel = 0; wsel < 2; wsel++) {
-            const int j = j0 + wa + wsel;
-            if (j < a.n_new) {
-                const float cost = m >= 2 ? (wsel == 0 ? DA[W + 1] : DB[W + 1]) : INFINITY;
-                const float normalized = __fdiv_rn(cost, (float)(2 * m));
-                a.scores[(b * a.n_new + j) * a.n_slots + s] =
-                    __fdiv_rn(1.f, 1.f + expf(__fdiv_rn(normalized - a.score_ref, a.score_ref)));
-            }
-        }
+    if (L.gate == 1) {
+        const int any = __syncthreads_or(pass ? 1 : 0);
+        if (tid == 0) *tile = any ? 1 : 0;
     }
 }
 
 }  // namespace
 
-int g_window_kernel = 0;  // 0/1 = one window per thread (default), 2 = two windows per thread, 3 = one window per thread with the
-                          // templates in shared memory even when they fit constant memory (A/B measurements)
-void set_dtw_window_kernel(int v) { g_window_kernel = v; }
+// 0 = templates from constant memory when they fit (default), 3 = always from shared memory (A/B measurements, debug only)
+std::atomic<int> g_window_kernel{0};
+void set_dtw_window_kernel(int v) { g_window_kernel.store(v); }
 
 // Unit-normalised templates are prepared by the engine (tmpl_unit has the layout of a.tmpl; tmpl_floats of them, tmpl_version
 // changes whenever their contents do).
@@ -560,28 +392,15 @@ bool const_templates_mine(int dev, const float* tmpl_unit, size_t tmpl_floats, u
     o.challenger = nullptr;
     return true;
 }
-}  // namespace
 
-cudaError_t launch_dtw_windows_d16(const DtwWindowsArgs& a, const float* tmpl_unit, size_t tmpl_floats, uint64_t tmpl_version,
-                                   cudaStream_t stream) {
-    if (a.d != kD || a.band != 5) return cudaErrorInvalidValue;
-    constexpr int W = 5;
-    const int j_blocks = (a.n_new - a.first_window + kNW - 1) / kNW;
-    if (j_blocks <= 0) return cudaSuccess;
-    const int64_t ctas = a.n_streams * (int64_t)j_blocks * a.n_slots;
+template <int W, bool MASK>
+cudaError_t launch_instance(const DtwWindowsArgs& a, const WindowLaunch& L, const float* tmpl_unit, size_t tmpl_floats, uint64_t tmpl_version,
+                            int j_blocks, cudaStream_t stream) {
+    const int64_t ctas = a.n_streams * (int64_t)j_blocks * L.n_slots;
     if (ctas <= 0) return cudaSuccess;
     if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
     const int x_rows = kNW + a.max_len + W + 1;
     const int p_rows = kNW + a.max_len + 1;
-    if (g_window_kernel == 2) {   // two windows per thread (measured slower on B200: 142 regs -> 8 DP warps/SM)
-        const size_t bytes2 = ((size_t)x_rows * kXS + (size_t)a.max_len * kD + 2 * (kNW + 2 * W + 2) + (kThreads2 / 16 + 2) * kD +
-                               (size_t)p_rows * kXS) * sizeof(float);
-        if (bytes2 > 200 * 1024) return cudaErrorInvalidValue;
-        cudaError_t e2 = cudaFuncSetAttribute(dtw_windows_d16x2_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes2);
-        if (e2 != cudaSuccess) return e2;
-        dtw_windows_d16x2_kernel<W><<<(unsigned)ctas, kThreads2, bytes2, stream>>>(a, tmpl_unit, x_rows, j_blocks);
-        return cudaGetLastError();
-    }
     const size_t bytes = ((size_t)x_rows * kXS + (size_t)a.max_len * kD + 2 * (kNW + 2 * W) + (kThreads / 16 + 1) * kD +
                           (size_t)p_rows * kD) * sizeof(float);
     if (bytes > 200 * 1024) return cudaErrorInvalidValue;
@@ -589,19 +408,48 @@ cudaError_t launch_dtw_windows_d16(const DtwWindowsArgs& a, const float* tmpl_un
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lock(g_const_mu);   // (the launch below happens while the ownership is known)
     cudaError_t e0 = cudaSuccess;
-    const bool ct = g_window_kernel != 3 && tmpl_floats > 0 && tmpl_floats <= (size_t)kConstRows * kD && dev >= 0 && dev < 64 &&
+    const bool ct = g_window_kernel.load() != 3 && tmpl_floats > 0 && tmpl_floats <= (size_t)kConstRows * kD && dev >= 0 && dev < 64 &&
                     const_templates_mine(dev, tmpl_unit, tmpl_floats, tmpl_version, stream, &e0);
     if (e0 != cudaSuccess) return e0;
     if (ct) {
-        cudaError_t e = cudaFuncSetAttribute(dtw_windows_d16_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cudaError_t e = cudaFuncSetAttribute(dtw_windows_d16_kernel<W, true, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
-        dtw_windows_d16_kernel<W, true><<<(unsigned)ctas, kThreads, bytes, stream>>>(a, tmpl_unit, x_rows, j_blocks);
+        dtw_windows_d16_kernel<W, true, MASK><<<(unsigned)ctas, kThreads, bytes, stream>>>(a, L, tmpl_unit, x_rows, j_blocks);
         return cudaGetLastError();
     }
-    cudaError_t e = cudaFuncSetAttribute(dtw_windows_d16_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    cudaError_t e = cudaFuncSetAttribute(dtw_windows_d16_kernel<W, false, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
-    dtw_windows_d16_kernel<W, false><<<(unsigned)ctas, kThreads, bytes, stream>>>(a, tmpl_unit, x_rows, j_blocks);
+    dtw_windows_d16_kernel<W, false, MASK><<<(unsigned)ctas, kThreads, bytes, stream>>>(a, L, tmpl_unit, x_rows, j_blocks);
     return cudaGetLastError();
+}
+}  // namespace
+
+bool dtw_windows_tuned_supported(int d, int band, int max_slot_len, int window_len) {
+    return d >= 1 && d <= kD && band >= 1 && band <= 20 && max_slot_len <= window_len && max_slot_len >= 1;
+}
+
+int dtw_windows_tile() { return kNW; }
+
+cudaError_t launch_dtw_windows_d16(const DtwWindowsArgs& a, const WindowGate& g, const float* tmpl_unit, size_t tmpl_floats,
+                                   uint64_t tmpl_version, cudaStream_t stream) {
+    if (!dtw_windows_tuned_supported(a.d, a.band, a.max_len, a.window_len > 0 ? a.window_len : a.max_len)) return cudaErrorInvalidValue;
+    const int j_blocks = (a.n_new - a.first_window + kNW - 1) / kNW;
+    if (j_blocks <= 0) return cudaSuccess;
+    WindowLaunch L;
+    L.slots = g.slots;
+    L.n_slots = g.slots ? g.n_slots : a.n_slots;
+    L.unit_off = g.unit_off;
+    L.gate = g.gate;
+    L.slot_ww = g.slot_ww;
+    L.metas = g.metas;
+    L.n_wakewords = g.n_wakewords;
+    L.tile_pass = g.tile_pass;
+    L.band = a.band;
+    if (a.band == 5) return launch_instance<5, false>(a, L, tmpl_unit, tmpl_floats, tmpl_version, j_blocks, stream);
+    if (a.band < 5) return launch_instance<5, true>(a, L, tmpl_unit, tmpl_floats, tmpl_version, j_blocks, stream);
+    if (a.band <= 8) return launch_instance<8, true>(a, L, tmpl_unit, tmpl_floats, tmpl_version, j_blocks, stream);
+    if (a.band <= 12) return launch_instance<12, true>(a, L, tmpl_unit, tmpl_floats, tmpl_version, j_blocks, stream);
+    return launch_instance<20, true>(a, L, tmpl_unit, tmpl_floats, tmpl_version, j_blocks, stream);
 }
 
 }  // namespace rp

@@ -128,18 +128,34 @@ void Engine::configure(const WakewordSet& ws, const rp_config& cfg) {
         tmpl.insert(tmpl.end(), m.v.begin(), m.v.end());
     }
     upload(tmpl_, tmpl, stream_, "templates");
-    {   // unit-length rows for the tuned kernels: a / sqrt(|a|^2), zero rows stay zero
-        std::vector<float> unit(tmpl.size());
-        for (size_t r = 0; r + d_ <= tmpl.size(); r += (size_t)d_) {
+    {   // unit-length rows for the tuned kernels: a / sqrt(|a|^2), zero rows stay zero; rows zero-padded to 16 floats
+        // (mfcc_size <= 16) so that one kernel instance serves every width
+        const int dp = d_ <= 16 ? 16 : d_;
+        std::vector<float> unit((tmpl.size() / (size_t)d_) * (size_t)dp, 0.f);
+        for (size_t r = 0, row = 0; r + d_ <= tmpl.size(); r += (size_t)d_, row++) {
             float n2 = 0.f;
             for (int k = 0; k < d_; k++) n2 += tmpl[r + k] * tmpl[r + k];
             const float inv = n2 > 0.f ? 1.f / std::sqrt(n2) : 0.f;
-            for (int k = 0; k < d_; k++) unit[r + k] = tmpl[r + k] * inv;
+            for (int k = 0; k < d_; k++) unit[row * dp + k] = tmpl[r + k] * inv;
         }
         upload(tmpl_unit_, unit, stream_, "unit templates");
         tmpl_unit_floats_ = unit.size();
         static std::atomic<uint64_t> next_version{1};
         tmpl_version_ = next_version++;
+        std::vector<int64_t> uoff;
+        for (int64_t o : off) uoff.push_back(o / d_ * dp);
+        upload(unit_off_, uoff, stream_, "unit template offsets");
+        // launch lists of the avg gate: avg_features slots first, then the template slots
+        std::vector<int32_t> avg_slots, tmpl_slots, slot_ww;
+        for (int s2 = 0; s2 < n_slots_; s2++) {
+            slot_ww.push_back(ws.slots[(size_t)s2].wakeword);
+            (ws.slots[(size_t)s2].tmpl < 0 ? avg_slots : tmpl_slots).push_back(s2);
+        }
+        n_avg_slots_ = (int)avg_slots.size();
+        n_tmpl_slots_ = (int)tmpl_slots.size();
+        upload(avg_slots_, avg_slots, stream_, "avg slots");
+        upload(tmpl_slots_, tmpl_slots, stream_, "template slots");
+        upload(slot_ww_, slot_ww, stream_, "slot wakewords");
     }
     upload(slot_off_, off, stream_, "slot offsets");
     upload(slot_len_, len, stream_, "slot lengths");
@@ -237,11 +253,13 @@ void Engine::ensure_frames(int n_new) {
     frames_cap_ = n_new;
 }
 
-void Engine::process(const float* audio, int64_t S, bool on_device, bool want_vad, int first_window,
-                     std::vector<HitRecord>& hits, std::vector<float>* vad) {
+void Engine::process(const AudioIn& in, bool want_vad, int first_window, std::vector<HitRecord>& hits, std::vector<float>* vad) {
     hits.clear();
     if (n_slots_ == 0) return;
     cuda_check(cudaSetDevice(device_), "cudaSetDevice");
+    const int64_t S = in.samples;
+    const bool on_device = in.on_device;
+    const bool decode = in.needs_decode();
     const int n_new = (int)(S / kHopSamples);
     ensure_frames(n_new);
     launches = 0;
@@ -256,8 +274,13 @@ void Engine::process(const float* audio, int64_t S, bool on_device, bool want_va
         vad_dev = vad_.as<float>();
     }
     const bool filters = filt_gain_ || filt_bp_;
-    if (!on_device || filters) audio_.reserve((size_t)n_streams_ * S * sizeof(float), "audio staging");
-    const float* src_all = (on_device && !filters) ? audio : audio_.as<float>();
+    if (!on_device || filters || decode) audio_.reserve((size_t)n_streams_ * S * sizeof(float), "audio staging");
+    const size_t raw_stream = in.bytes_per_stream();
+    if (!on_device && decode) raw_.reserve((size_t)n_streams_ * raw_stream, "raw audio staging");
+    // what K1 (or the filter stage) reads: the caller's f32 device audio as it is, everything else through the f32 staging buffer
+    const float* f32_in = (on_device && !decode) ? static_cast<const float*>(in.data) : audio_.as<float>();
+    const float* src_all = filters ? audio_.as<float>() : f32_in;
+    const uint8_t* raw_all = !decode ? nullptr : (on_device ? static_cast<const uint8_t*>(in.data) : raw_.as<uint8_t>());
     const int n_chunks = (int)(S / kFrameSamples);
     if (filt_gain_) gains_.reserve((size_t)n_streams_ * n_chunks * sizeof(float), "gains");
 
@@ -274,22 +297,39 @@ void Engine::process(const float* audio, int64_t S, bool on_device, bool want_va
     cuda_check(cudaEventRecord(ev_[0], stream_), "event");
     if (!on_device) {
         cuda_check(cudaStreamWaitEvent(copy_stream_, ev_[0], 0), "wait");
+        const uint8_t* host = static_cast<const uint8_t*>(in.data);
+        uint8_t* dst = decode ? raw_.as<uint8_t>() : reinterpret_cast<uint8_t*>(audio_.as<float>());
         for (int g = 0; g < n_groups; g++) {
             const int64_t b0 = g * gs, nb = std::min(gs, n_streams_ - b0);
-            cuda_check(cudaMemcpyAsync(audio_.as<float>() + b0 * S, audio + b0 * S, (size_t)nb * S * sizeof(float),
+            cuda_check(cudaMemcpyAsync(dst + (size_t)b0 * raw_stream, host + (size_t)b0 * raw_stream, (size_t)nb * raw_stream,
                                        cudaMemcpyHostToDevice, copy_stream_), "H2D audio");
             cuda_check(cudaEventRecord(group_ev_[4 * g], copy_stream_), "event");
         }
     }
+    // avg gate: tile verdicts of this call
+    const bool tuned = dtw_variant_ != 1 && dtw_windows_tuned_supported(d_, band_, max_slot_len_, max_frames_);
+    const int fw = std::min(std::max(first_window, 0), n_new);
+    const int tile = dtw_windows_tile();
+    const int j_blocks = (n_new - fw + tile - 1) / tile;
+    const bool gated = tuned && avg_gate_ && n_avg_slots_ > 0 && n_tmpl_slots_ > 0 && j_blocks > 0;
+    if (gated) tile_pass_.reserve((size_t)n_streams_ * j_blocks * n_wakewords_, "avg-gate tiles");
+    last_gated_ = gated;
+    last_j_blocks_ = j_blocks;
+    last_first_window_ = fw;
     cuda_check(cudaMemsetAsync(hit_count_.as<void>(), 0, sizeof(int), stream_), "memset");
     float* fb_all = frames_[cur_].as<float>();
     for (int g = 0; g < n_groups; g++) {
         const int64_t b0 = g * gs, nb = std::min(gs, n_streams_ - b0);
         if (!on_device) cuda_check(cudaStreamWaitEvent(stream_, group_ev_[4 * g], 0), "wait");
         cuda_check(cudaEventRecord(group_ev_[4 * g + 1], stream_), "event");
+        if (decode) {  // Sample::into_f32 + channel 0 (audio_types.rs:98-137, encoder.rs:41-48) -> f32 staging
+            cuda_check(launch_decode_samples(raw_all + (size_t)b0 * raw_stream, (int64_t)raw_stream, in.fmt, in.channels, in.big_endian ? 1 : 0,
+                                             audio_.as<float>() + b0 * S, S, nb, S, stream_), "decode kernel");
+            launches += 1;
+        }
         if (filters) {  // gain normaliser / band pass: caller's (or staged) audio -> staging buffer
             FilterArgs fa;
-            fa.in = (on_device ? audio : audio_.as<float>()) + b0 * S;
+            fa.in = f32_in + b0 * S;
             fa.in_stride = S;
             fa.out = audio_.as<float>() + b0 * S;
             fa.out_stride = S;
@@ -333,14 +373,40 @@ void Engine::process(const float* audio, int64_t S, bool on_device, bool want_va
         wa.slot_len = slot_len_.as<int32_t>();
         wa.n_slots = n_slots_;
         wa.max_len = max_slot_len_;
+        wa.window_len = max_frames_;
         wa.band = band_;
         wa.score_ref = score_ref_;
         wa.scores = tscore_.as<float>() + b0 * (int64_t)n_new * n_slots_;
-        wa.first_window = std::min(std::max(first_window, 0), n_new);
-        if (d_ == 16 && band_ == 5 && dtw_variant_ != 1)
-            cuda_check(launch_dtw_windows_d16(wa, tmpl_unit_.as<float>(), tmpl_unit_floats_, tmpl_version_, stream_), "dtw window kernel");
-        else
+        wa.first_window = fw;
+        if (wa.first_window > 0)   // rows no kernel writes read as NaN in rp_batch_copy_last_scores
+            cuda_check(cudaMemset2DAsync(wa.scores, (size_t)n_new * n_slots_ * sizeof(float), 0xff,
+                                         (size_t)wa.first_window * n_slots_ * sizeof(float), (size_t)nb, stream_), "memset skipped rows");
+        // (an avg_features matrix longer than every template scores a window shorter than itself: generic kernel only)
+        if (tuned) {
+            WindowGate wg;
+            wg.unit_off = unit_off_.as<int64_t>();
+            wg.slot_ww = slot_ww_.as<int32_t>();
+            wg.metas = metas_.as<WakewordMeta>();
+            wg.n_wakewords = n_wakewords_;
+            if (gated) {
+                // wakeword_comp.rs:85-94: avg_features first; templates only where some window of the tile passes the avg gate
+                wg.tile_pass = tile_pass_.as<unsigned char>() + (size_t)b0 * j_blocks * n_wakewords_;
+                cuda_check(cudaMemsetAsync(wg.tile_pass, 1, (size_t)nb * j_blocks * n_wakewords_, stream_), "memset tiles");
+                wg.slots = avg_slots_.as<int32_t>();
+                wg.n_slots = n_avg_slots_;
+                wg.gate = 1;
+                cuda_check(launch_dtw_windows_d16(wa, wg, tmpl_unit_.as<float>(), tmpl_unit_floats_, tmpl_version_, stream_), "dtw window kernel (avg)");
+                wg.slots = tmpl_slots_.as<int32_t>();
+                wg.n_slots = n_tmpl_slots_;
+                wg.gate = 2;
+                cuda_check(launch_dtw_windows_d16(wa, wg, tmpl_unit_.as<float>(), tmpl_unit_floats_, tmpl_version_, stream_), "dtw window kernel (templates)");
+                launches += 1;
+            } else {
+                cuda_check(launch_dtw_windows_d16(wa, wg, tmpl_unit_.as<float>(), tmpl_unit_floats_, tmpl_version_, stream_), "dtw window kernel");
+            }
+        } else {
             cuda_check(launch_dtw_windows_generic(wa, stream_), "dtw kernel");
+        }
         JudgeArgs ja;
         ja.scores = wa.scores;
         ja.n_streams = nb;
@@ -419,6 +485,42 @@ void Engine::process(const float* audio, int64_t S, bool on_device, bool want_va
     std::sort(hits.begin(), hits.end(), [](const HitRecord& a, const HitRecord& b) {
         return a.stream != b.stream ? a.stream < b.stream : a.frame < b.frame;
     });
+}
+
+void Engine::last_gate_stats(int64_t* tiles, int64_t* passed) const {
+    int64_t t = 0, p = 0;
+    if (last_gated_) {
+        cuda_check(cudaSetDevice(device_), "cudaSetDevice");
+        std::vector<unsigned char> h((size_t)n_streams_ * last_j_blocks_ * n_wakewords_);
+        cuda_check(cudaMemcpy(h.data(), tile_pass_.as<void>(), h.size(), cudaMemcpyDeviceToHost), "D2H avg-gate tiles");
+        t = (int64_t)h.size();
+        for (unsigned char v : h) p += v ? 1 : 0;
+    }
+    if (tiles) *tiles = t;
+    if (passed) *passed = p;
+}
+
+void Engine::copy_last_scores(float* out) const {
+    const int64_t n = n_streams_ * (int64_t)last_n_new_ * n_slots_;
+    if (n <= 0) return;
+    cuda_check(cudaSetDevice(device_), "cudaSetDevice");
+    cuda_check(cudaMemcpy(out, tscore_.as<void>(), (size_t)n * sizeof(float), cudaMemcpyDeviceToHost), "D2H scores");
+    if (!last_gated_) return;
+    // template slots of the tiles the avg gate skipped were never written
+    std::vector<unsigned char> h((size_t)n_streams_ * last_j_blocks_ * n_wakewords_);
+    cuda_check(cudaMemcpy(h.data(), tile_pass_.as<void>(), h.size(), cudaMemcpyDeviceToHost), "D2H avg-gate tiles");
+    std::vector<int32_t> tmpl_slots((size_t)n_tmpl_slots_), slot_ww((size_t)n_slots_);
+    cuda_check(cudaMemcpy(tmpl_slots.data(), tmpl_slots_.as<void>(), tmpl_slots.size() * sizeof(int32_t), cudaMemcpyDeviceToHost), "D2H");
+    cuda_check(cudaMemcpy(slot_ww.data(), slot_ww_.as<void>(), slot_ww.size() * sizeof(int32_t), cudaMemcpyDeviceToHost), "D2H");
+    const int tile = dtw_windows_tile();
+    const float nan = std::nanf("");
+    for (int64_t b = 0; b < n_streams_; b++)
+        for (int j = last_first_window_; j < last_n_new_; j++) {
+            const int jb = (j - last_first_window_) / tile;
+            for (int32_t s : tmpl_slots)
+                if (!h[(size_t)(b * last_j_blocks_ + jb) * n_wakewords_ + slot_ww[(size_t)s]])
+                    out[(b * last_n_new_ + j) * n_slots_ + s] = nan;
+        }
 }
 
 }  // namespace rp

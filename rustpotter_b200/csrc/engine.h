@@ -50,6 +50,19 @@ struct HitRecord {     // one judged detection of K3, host copy
     const float* scores;  // into Engine::hit_host_
 };
 
+// One call's audio: [n_streams][samples * channels] interleaved samples of `fmt`, host or device memory.
+struct AudioIn {
+    const void* data = nullptr;
+    int fmt = RP_FMT_F32;      // RP_FMT_*: what `data` holds
+    int channels = 1;          // interleaved channels; channel 0 is used (encoder.rs:41-48)
+    bool big_endian = false;   // byte order of multi-byte samples in `data`
+    bool on_device = false;
+    int64_t samples = 0;       // MONO samples per stream (a multiple of 480)
+    size_t bytes_per_sample() const { return fmt == RP_FMT_I8 ? 1 : fmt == RP_FMT_I16 ? 2 : 4; }
+    size_t bytes_per_stream() const { return (size_t)samples * channels * bytes_per_sample(); }
+    bool needs_decode() const { return fmt != RP_FMT_F32 || channels != 1 || big_endian; }
+};
+
 class Engine {
   public:
     Engine(int device, int64_t n_streams);
@@ -64,6 +77,9 @@ class Engine {
     // Uploads templates / tables for the wakeword set; keeps per-stream frame history.
     void configure(const WakewordSet& ws, const rp_config& cfg);
     void set_dtw_variant(int v) { dtw_variant_ = v; }
+    // Avg gate of the tuned window kernel (wakeword_comp.rs:85-94): true = avg slots first, template slots only for the
+    // window tiles in which some window passes (default); false = every slot of every window (dense score tensor).
+    void set_avg_gate(bool on) { avg_gate_ = on; }
     // FiltersConfig (src/config.rs:31-84): fresh filter state for every stream (update_filters_config semantics:
     // the gain reference is NOT re-derived from the wakewords until set_gain_reference is called again).
     void set_filters(const rp_config& cfg);
@@ -76,8 +92,13 @@ class Engine {
     // Scores samples_per_stream/160 new hops per stream. Returns the hits sorted by (stream, frame);
     // `vad` (if want_vad) receives [n_streams][n_hops] mean |mfcc| per new frame.
     // first_window: no stream can use the windows that end before this new hop (fresh / just-reset streams).
-    void process(const float* audio, int64_t samples_per_stream, bool on_device, bool want_vad, int first_window,
-                 std::vector<HitRecord>& hits, std::vector<float>* vad);
+    void process(const AudioIn& in, bool want_vad, int first_window, std::vector<HitRecord>& hits, std::vector<float>* vad);
+    // Avg-gate statistics of the last process(): (stream, 128-window block, wakeword) tiles and how many of them had a
+    // window that passed the avg gate (the template slots of the others were skipped). 0/0 when the gate was off.
+    void last_gate_stats(int64_t* tiles, int64_t* passed) const;
+    // Host copy of the last call's dense scores; entries of gated-out tiles (never computed) and of the skipped leading
+    // windows are NaN.
+    void copy_last_scores(float* out_host) const;
 
     // diagnostics
     float timings_ms[5] = {0, 0, 0, 0, 0};
@@ -98,12 +119,18 @@ class Engine {
     std::vector<cudaEvent_t> group_ev_;   // [group][4]: copy done, start, after MFCC, after DTW/judge
     int group_streams_ = 256;             // streams per pipeline group (RP_GROUP_STREAMS)
     int dtw_variant_ = 0;
+    bool avg_gate_ = true;
 
     // wakeword set on device
     int d_ = 0, max_frames_ = 0, n_slots_ = 0, n_wakewords_ = 0, max_templates_ = 0, max_slot_len_ = 0;
     int band_ = 5, score_mode_ = 1;
     float score_ref_ = 0.22f;
     DeviceBuffer tmpl_, tmpl_unit_, slot_off_, slot_len_, metas_;
+    DeviceBuffer unit_off_, avg_slots_, tmpl_slots_, slot_ww_;   // tuned window kernel: padded-template offsets, launch lists
+    int n_avg_slots_ = 0, n_tmpl_slots_ = 0;
+    DeviceBuffer tile_pass_;   // [B][j_blocks][n_wakewords] avg-gate verdict per window tile
+    int last_j_blocks_ = 0, last_first_window_ = 0;
+    bool last_gated_ = false;
     size_t tmpl_unit_floats_ = 0;   // floats in tmpl_unit_
     uint64_t tmpl_version_ = 0;     // changes with every upload of the templates (the window kernel's constant-memory copy follows it)
     // MFCC tables on device
@@ -115,7 +142,8 @@ class Engine {
     int hist_ = 0;             // history rows kept in front of the new frames (= max_frames - 1)
     int frames_cap_ = 0;       // new-frame capacity per stream
     // per-call
-    DeviceBuffer audio_;       // [B][S] staging for host audio
+    DeviceBuffer audio_;       // [B][S] f32 staging (host audio, decoded samples, filter output)
+    DeviceBuffer raw_;         // [B][S * channels * bytes] staging for host audio that needs decoding
     DeviceBuffer tscore_;      // [B][n_new][n_slots]
     DeviceBuffer vad_;         // [B][n_new]
     DeviceBuffer hits_;        // [cap][5 + max_templates]

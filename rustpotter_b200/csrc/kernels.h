@@ -83,17 +83,31 @@ struct DtwWindowsArgs {
     const int32_t* slot_len = nullptr; // [n_slots] rows
     int n_slots = 0;
     int max_len = 0;                   // max slot_len
+    int window_len = 0;                // max_mfcc_frames: rows of a stream's window (the longest TEMPLATE; avg_features may be longer)
     int band = 5;
     float score_ref = 0.22f;
     float* scores = nullptr;           // [n_streams][n_new][n_slots]
     int first_window = 0;              // windows j < first_window are not scored (no stream can use them)
 };
 cudaError_t launch_dtw_windows_generic(const DtwWindowsArgs& a, cudaStream_t stream);
-// Tuned variant for d == 16, band == 5 (dtw_window_kernel.cu). tmpl_unit: the templates of a.tmpl with every row
-// scaled to unit length (zero rows stay zero), same offsets.
-cudaError_t launch_dtw_windows_d16(const DtwWindowsArgs& a, const float* tmpl_unit, size_t tmpl_floats, uint64_t tmpl_version,
-                                   cudaStream_t stream);
-void set_dtw_window_kernel(int v);  // 0/1 = one window per thread (default), 2 = two windows per thread, 3 = templates from shared memory
+// Tuned variant for d <= 16, band 1..20, slot_len <= window_len (dtw_window_kernel.cu). tmpl_unit: the templates with every
+// row scaled to unit length (zero rows stay zero) and zero-padded to 16 floats; g.unit_off[s] = offset of slot s in it.
+// Which slots a launch covers and the avg gate (wakeword_comp.rs:85-94) are described by WindowGate (device pointers).
+struct WindowGate {
+    const int64_t* unit_off = nullptr;   // [n_slots]
+    const int32_t* slots = nullptr;      // slot ids of this launch (nullptr: all of a.n_slots)
+    int n_slots = 0;
+    int gate = 0;                        // 0 none; 1 these are avg slots: write tile_pass; 2 template slots: skip tiles without a pass
+    const int32_t* slot_ww = nullptr;    // [n_slots] wakeword of a slot
+    const WakewordMeta* metas = nullptr;
+    int n_wakewords = 0;
+    unsigned char* tile_pass = nullptr;  // [n_streams][ceil((n_new - first_window) / dtw_windows_tile())][n_wakewords]
+};
+bool dtw_windows_tuned_supported(int d, int band, int max_slot_len, int window_len);
+int dtw_windows_tile();                  // windows per CTA tile (the granularity of the avg gate)
+cudaError_t launch_dtw_windows_d16(const DtwWindowsArgs& a, const WindowGate& g, const float* tmpl_unit, size_t tmpl_floats,
+                                   uint64_t tmpl_version, cudaStream_t stream);
+void set_dtw_window_kernel(int v);  // 0 = templates from constant memory when they fit, 3 = always shared memory (debug)
 
 // K3: judge every window, append detections to a compact hit list.
 // hit record (floats/ints, stride = 5 + max_templates): [stream, frame, wakeword, avg_score, score, scores...]
@@ -135,6 +149,11 @@ struct FilterArgs {
     float* bp_state = nullptr;     // [n_streams][4] x1 x2 y1 y2
 };
 cudaError_t launch_audio_filters(const FilterArgs& a, cudaStream_t stream);
+
+// Sample decoding in front of the filters / MFCC kernel (audio_types.rs:98-137, encoder.rs:26-50): raw interleaved samples
+// of RP_FMT_* (big_endian: byte order of the source) -> channel 0 as f32. in: [n_streams][in_stride_bytes], out: [n_streams][out_stride].
+cudaError_t launch_decode_samples(const void* in, int64_t in_stride_bytes, int fmt, int channels, int big_endian, float* out,
+                                  int64_t out_stride, int64_t n_streams, int64_t samples_mono, cudaStream_t stream);
 
 // misc small kernels
 cudaError_t launch_copy_rows(const float* src, int64_t src_stride, float* dst, int64_t dst_stride, int64_t n_streams,

@@ -43,12 +43,13 @@ class Cursor {
     bool at_null() const { return p_ < end_ && (*p_ == 0xf6 || *p_ == 0xf7); }
     void eat() { byte(); }
 
-    std::string text() {
+    std::string text(bool chunk = false) {
         Head h = head();
         if (h.major != kText) fail("expected a text string");
         if (h.arg == kIndefinite) {
+            if (chunk) fail("nested indefinite-length string chunk");   // RFC 8949 3.2.3: chunks are definite
             std::string s;
-            while (!at_break()) s += text();
+            while (!at_break()) s += text(true);
             eat_break();
             return s;
         }
@@ -87,25 +88,35 @@ class Cursor {
         }
     }
 
-    void skip() {
+    // Skips one data item. Nesting is bounded (untrusted input must not overflow the host stack).
+    void skip(int depth = 0) {
+        if (depth > kMaxDepth) fail("CBOR nesting too deep");
         Head h = head();
         switch (h.major) {
             case kUInt: case kNInt: case kSimple: return;
             case kBytes: case kText:
-                if (h.arg == kIndefinite) { while (!at_break()) skip(); eat_break(); }
-                else { need(h.arg); p_ += h.arg; }
+                if (h.arg == kIndefinite) {
+                    while (!at_break()) {   // definite chunks of the same major type only
+                        Head ch = head();
+                        if (ch.major != h.major || ch.arg == kIndefinite) fail("bad chunk in an indefinite-length string");
+                        need(ch.arg);
+                        p_ += ch.arg;
+                    }
+                    eat_break();
+                } else { need(h.arg); p_ += h.arg; }
                 return;
             case kArray:
-                if (h.arg == kIndefinite) { while (!at_break()) skip(); eat_break(); }
-                else for (uint64_t i = 0; i < h.arg; i++) skip();
+                if (h.arg == kIndefinite) { while (!at_break()) skip(depth + 1); eat_break(); }
+                else for (uint64_t i = 0; i < h.arg; i++) skip(depth + 1);
                 return;
             case kMap:
-                if (h.arg == kIndefinite) { while (!at_break()) { skip(); skip(); } eat_break(); }
-                else for (uint64_t i = 0; i < h.arg; i++) { skip(); skip(); }
+                if (h.arg == kIndefinite) { while (!at_break()) { skip(depth + 1); skip(depth + 1); } eat_break(); }
+                else for (uint64_t i = 0; i < h.arg; i++) { skip(depth + 1); skip(depth + 1); }
                 return;
-            case kTag: skip(); return;
+            case kTag: skip(depth + 1); return;
         }
     }
+    static constexpr int kMaxDepth = 64;
 
     [[noreturn]] void fail(const char* what) const { throw Error(RP_ERR_FORMAT, std::string("wakeword file: ") + what); }
 

@@ -146,6 +146,7 @@ bool StreamState::run_detection(const DetectorParams& p, const Hit* hit, float g
         if (!partial_ || partial_->score < hit->score) {
             PartialDetection d;
             d.wakeword = hit->wakeword;
+            d.names = hit->names;
             d.avg_score = hit->avg_score;
             d.score = hit->score;
             d.counter = counter;

@@ -4,6 +4,7 @@
 // reset-after-detection) and src/mfcc/vad.rs:11-49 on top of hop-indexed kernel output.
 #pragma once
 
+#include <memory>
 #include <optional>
 #include <string>
 #include <vector>
@@ -39,6 +40,15 @@ struct WakewordSet {
     const FrameMatrix& slot_matrix(int slot) const;
 };
 
+// Name of a wakeword and of its templates, snapshotted when the wakeword set changes. A pending partial detection
+// keeps its snapshot by value (shared), as the reference keeps `name` and the `scores` keys inside the
+// RustpotterDetection (detector.rs:487-501): removing or replacing the wakeword later cannot invalidate it.
+struct WakewordNames {
+    std::string name;
+    std::vector<std::string> templates;
+    std::vector<const char*> template_cstrs;   // into `templates`
+};
+
 // A window judged as a detection by K3 (or by judge_window on the host).
 struct Hit {
     int64_t stream;
@@ -48,10 +58,12 @@ struct Hit {
     float score;
     const float* scores;  // n_scores values (the wakeword's templates, file order)
     int32_t n_scores;
+    std::shared_ptr<const WakewordNames> names;  // of `wakeword` at the time of the hit (may be null in host-only replays)
 };
 
 struct PartialDetection {
-    int wakeword = -1;
+    int wakeword = -1;                           // index at the time of the hit; only `names` is used afterwards
+    std::shared_ptr<const WakewordNames> names;
     float avg_score = 0.f, score = 0.f;
     std::vector<float> scores;
     uint64_t counter = 0;

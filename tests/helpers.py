@@ -112,3 +112,20 @@ def splice(audio: np.ndarray, utt: np.ndarray, hop_offset: int) -> None:
     """Overwrites audio[hop_offset*160 : ...] with an utterance (in place)."""
     s = hop_offset * 160
     audio[s: s + utt.size] = utt
+
+
+# BASELINE configs[4] ("config 5"): four WakewordRefs, 8 templates (+ avg_features) each, D = 16, ~1 s templates
+CONFIG5_NAMES = ("hey b200", "ok blackwell", "wake nvlink", "hello hbm")
+CONFIG5_LENGTHS = ((88, 92, 96, 100, 100, 96, 92, 100), (84, 90, 94, 98, 100, 96, 88, 92),
+                   (90, 100, 86, 94, 98, 92, 96, 100), (96, 88, 100, 92, 90, 98, 94, 86))
+CONFIG5_SEEDS = (1234, 2345, 3456, 4567)
+
+
+def make_config5_wakewords(oracle, d=16):
+    """Returns ([rpw bytes] * 4, [[utterances of wakeword w]] * 4)."""
+    rpws, utts = [], []
+    for name, lengths, seed in zip(CONFIG5_NAMES, CONFIG5_LENGTHS, CONFIG5_SEEDS):
+        r, u = make_wakeword(oracle, name=name, d=d, lengths=lengths, seed=seed)
+        rpws.append(r)
+        utts.append(u)
+    return rpws, utts

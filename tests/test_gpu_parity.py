@@ -472,18 +472,36 @@ def test_window_scores_tuned_vs_generic_vs_oracle(lengths):
     audio[1, 20000:30000] *= np.float32(0.01)          # a quiet stretch (large |mean| / |deviation| ratio)
     T, maxf = len(lengths), max(lengths)
     res = {}
-    for variant in (1, 2, 4):   # generic / one window per thread (default) / two windows per thread
+    rp.set_avg_gate(0)                                  # dense: every template of every window
+    for variant in (1, 2):   # generic / tuned pipeline kernel (default)
         rp.set_dtw_variant(variant)
         bt = rp.RustpotterBatch(3)
         bt.add_wakeword_from_buffer("w", rpw)
         bt.process(audio)
         res[variant] = bt.last_scores(n_chunks * 3, T + 1)
     rp.set_dtw_variant(0)
+    rp.set_avg_gate(-1)
+    # default mode (avg gate first): what was computed is bit-identical, what was skipped reads NaN and would have
+    # failed the avg gate (avg_threshold 0.2) in every window of its 128-window tile
+    bt = rp.RustpotterBatch(3)
+    bt.add_wakeword_from_buffer("w", rpw)
+    bt.process(audio)
+    gated = bt.last_scores(n_chunks * 3, T + 1)
+    tiles, passed = bt.last_gate_stats()
+    assert tiles > 0 and 0 < passed <= tiles
+    first_all = max(lengths) + 2
+    g, dn = gated[:, first_all:], res[2][:, first_all:]
+    skipped = np.isnan(g)
+    assert not skipped[:, :, 0].any() and np.array_equal(g[~skipped], dn[~skipped])
+    for b in range(3):
+        for j0 in range(0, g.shape[1], 128):
+            if skipped[b, j0:j0 + 128, 1:].any():
+                assert skipped[b, j0:j0 + 128, 1:].all() and (dn[b, j0:j0 + 128, 0] < 0.2).all()
     first = maxf + 2                                    # hop of the first window a fresh detector scores
     for b in range(3):
         tr = O.trace_window_scores(O.default_config(), rpw, audio[b], T)   # [avg, agg, s...]
         want = np.concatenate([tr[:, :1], tr[:, 2:]], axis=1)
-        for variant, tol in ((1, 5e-6), (2, SCORE_RTOL), (4, SCORE_RTOL)):
+        for variant, tol in ((1, 5e-6), (2, SCORE_RTOL)):
             got = res[variant][b, first:]
             assert got.shape == want.shape
             rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-12)
@@ -502,6 +520,7 @@ def test_window_kernel_constant_templates_change_hands():
 
     def run(variant):
         rp.set_dtw_variant(variant)
+        rp.set_avg_gate(0)
         a, b = rp.RustpotterBatch(2), rp.RustpotterBatch(2)
         a.add_wakeword_from_buffer("a", rpw_a)
         b.add_wakeword_from_buffer("b", rpw_b)
@@ -513,6 +532,7 @@ def test_window_kernel_constant_templates_change_hands():
             b.process(au)                    # 66 launches of b alone in the middle: it takes the copy over
             out.append(b.last_scores(n_chunks * 3, 5).copy())
         rp.set_dtw_variant(0)
+        rp.set_avg_gate(-1)
         return out
 
     got, want = run(0), run(7)

@@ -375,3 +375,11 @@ def test_stream4_control_words():
                     B += 4
                     prev_active = False
     assert n_checked > 2000
+
+
+def test_cbor_reader_rejects_deep_nesting_without_recursing():
+    """1 MB of nested arrays / tags must fail with RP_ERR_FORMAT, not overflow the host stack (advisor finding)."""
+    for byte in (0x81, 0xC0, 0x9F, 0x7F):
+        with pytest.raises(rp.RustpotterError) as e:
+            rp.wakeword_inspect(bytes([0xA1, 0x61, 0x78]) + bytes([byte]) * (1 << 20))
+        assert e.value.code == -3
