@@ -71,7 +71,7 @@ def test_config5_four_wakewords_median_matches_oracle(kw, gated):
 def test_config5_device_audio_i16_and_sharded_handles_agree():
     """The same streams as i16 (Sample::into_f32 on the device: audio_types.rs:98-137) on one handle, and split over
     two handles (contiguous shards, what a multi-GPU run does per device): identical detections."""
-    rpws, audio = _config5_case(B=32, n_chunks=100)
+    rpws, audio = _config5_case(B=32)
     pcm = np.clip(np.round(audio * 32767.0), -32768, 32767).astype(np.int16)
     want_audio = pcm.astype(np.float32) / np.float32(32767.0)
     cfg = rp.default_config(score_mode="median")
@@ -263,7 +263,7 @@ def test_multi_device_handle_matches_single_device():
     import torch
     n_dev = torch.cuda.device_count()
     devices = [0, 1 % n_dev, 0] if n_dev >= 1 else [0]
-    rpws, audio = _config5_case(B=20, n_chunks=100)
+    rpws, audio = _config5_case(B=20)
     cfg = rp.default_config(score_mode="median")
     one = rp.RustpotterBatch(20, cfg)
     multi = rp.RustpotterBatch(20, cfg, devices=devices)
