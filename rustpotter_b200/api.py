@@ -314,7 +314,7 @@ class RustpotterBatch:
     def _dets(self, dets, n):
         return [(int(dets[i].stream), int(dets[i].chunk), dets[i].det.to_dict()) for i in range(n.value)]
 
-    def process_ptr(self, ptr: int, samples_per_stream: int, on_device: bool, fmt: str = "f32"):
+    def process_ptr(self, ptr: int, samples_per_stream: int, on_device: bool, fmt: str = "f32", parse: bool = True):
         """audio at raw address `ptr` ([n_streams][samples_per_stream] of `fmt`: i8/i16/i32/f32, interleaved channels)."""
         dets = C.POINTER(CBatchDetection)()
         n = C.c_int64()
@@ -323,22 +323,27 @@ class RustpotterBatch:
         else:
             _check(self._L.rp_batch_process_samples(self._h, C.c_void_p(ptr), SAMPLE_FORMATS[fmt], samples_per_stream, int(on_device),
                                                     C.byref(dets), C.byref(n)), self._h)
-        return self._dets(dets, n)
+        return self._dets(dets, n) if parse else int(n.value)
 
-    def process(self, audio):
+    def process_count(self, audio) -> int:
+        """process() without building Python objects: returns the number of detections of the call (the
+        rp_batch_detection records stay readable through the C ABI until the next call)."""
+        return self.process(audio, parse=False)
+
+    def process(self, audio, parse: bool = True):
         """process_samples<T> for every stream. audio: [n_streams][S] int8/int16/int32/float32 — a host numpy array or a
         torch tensor (CPU pinned/pageable or CUDA)."""
         if hasattr(audio, "data_ptr"):  # torch tensor
             import torch
             fmt = {torch.float32: "f32", torch.int16: "i16", torch.int32: "i32", torch.int8: "i8"}[audio.dtype]
             assert audio.is_contiguous() and audio.shape[0] == self.n_streams
-            return self.process_ptr(audio.data_ptr(), int(audio.shape[1]), audio.is_cuda, fmt)
+            return self.process_ptr(audio.data_ptr(), int(audio.shape[1]), audio.is_cuda, fmt, parse)
         a = np.ascontiguousarray(audio)
         fmt = {np.dtype(np.float32): "f32", np.dtype(np.int16): "i16", np.dtype(np.int32): "i32", np.dtype(np.int8): "i8"}.get(a.dtype)
         if fmt is None:
             a, fmt = np.ascontiguousarray(audio, dtype=np.float32), "f32"
         assert a.shape[0] == self.n_streams
-        return self.process_ptr(a.ctypes.data, a.shape[1], False, fmt)
+        return self.process_ptr(a.ctypes.data, a.shape[1], False, fmt, parse)
 
     def process_bytes(self, audio_bytes, bytes_per_stream: int | None = None, on_device: bool = False):
         """process_bytes for every stream: raw bytes in the config's sample format / endianness / channels.

@@ -84,14 +84,12 @@ def synth_utterance(seed: int, n_frames: int) -> np.ndarray:
     return x
 
 
-def make_wakeword(oracle, name="hey b200", d=16, lengths=(88, 92, 96, 100, 100, 96, 92, 100), seed=1234,
-                  threshold=None, avg_threshold=None, with_avg=True):
-    """Synthetic WakewordRef (SURVEY §8d config 2): templates are the ORACLE's MFCC + CMN of synthetic
-    utterances (so they are realistic mean-normalised cepstra). Returns (rpw bytes, utterances)."""
-    utts, tmpl = [], []
+def wakeword_utterances(lengths=(88, 92, 96, 100, 100, 96, 92, 100), seed=1234):
+    """The synthetic utterances a wakeword's templates are made from: variations of one "word" — time-trimmed, slightly
+    noised copies of one base utterance; utterance i gives exactly lengths[i] MFCC frames. Pure numpy (deterministic)."""
+    utts = []
     base = synth_utterance(seed, max(lengths))
     for i, n in enumerate(lengths):
-        # variations of one "word": time-trimmed, slightly noised copies of the base utterance
         rng = np.random.default_rng(seed + 17 * i + 1)
         off = int(rng.integers(0, max(lengths) - n + 1)) * 160
         u = base[off: off + (n + 3) * 160].copy()
@@ -99,7 +97,15 @@ def make_wakeword(oracle, name="hey b200", d=16, lengths=(88, 92, 96, 100, 100, 
         u = u.astype(np.float32)
         u[u == 0] = np.float32(1e-4)
         utts.append(u)
-        tmpl.append((f"sample_{i}.wav", oracle.normalize(oracle.mfcc_stream(u, d))))
+    return utts
+
+
+def make_wakeword(oracle, name="hey b200", d=16, lengths=(88, 92, 96, 100, 100, 96, 92, 100), seed=1234,
+                  threshold=None, avg_threshold=None, with_avg=True):
+    """Synthetic WakewordRef (SURVEY §8d config 2): templates are the ORACLE's MFCC + CMN of synthetic
+    utterances (so they are realistic mean-normalised cepstra). Returns (rpw bytes, utterances)."""
+    utts = wakeword_utterances(lengths, seed)
+    tmpl = [(f"sample_{i}.wav", oracle.normalize(oracle.mfcc_stream(u, d))) for i, u in enumerate(utts)]
     avg = None
     if with_avg:
         longest = max(tmpl, key=lambda t: t[1].shape[0])[1]

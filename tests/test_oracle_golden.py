@@ -3,6 +3,8 @@ not need the (un-vendored) rubato resampler, and the template matrices inside th
 fixtures (the reference's own MFCC + CMN output for the fixture wavs, tests/wakeword.rs:26-54).
 Expected values are the f32 literals asserted by the reference (tests/detector.rs, cited per test).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -214,3 +216,17 @@ def test_process_wrong_length_returns_none():  # detector.rs:235-237,249-251
     assert det.process_samples(np.zeros(479, np.int16)) is None
     det2 = O.Detector(O.default_config())
     assert det2.process_samples(np.zeros(480, np.float32)) is None  # no wakeword loaded
+
+
+def test_bench_template_fixture_is_the_oracles_mfcc():
+    """tests/golden/bench_templates.npz (what both arms of bench.py score against) equals the oracle's MFCC + CMN of
+    the deterministic utterances it was generated from (tools/make_bench_templates.py)."""
+    from tests.helpers import CONFIG5_LENGTHS, CONFIG5_SEEDS, wakeword_utterances
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bench_templates.npz"))
+    assert len(z.files) == 32
+    for w in (0, 3):
+        for i, u in enumerate(wakeword_utterances(CONFIG5_LENGTHS[w], CONFIG5_SEEDS[w])):
+            want = O.normalize(O.mfcc_stream(u, 16))
+            got = z[f"w{w}_t{i}"]
+            assert got.shape == want.shape == (CONFIG5_LENGTHS[w][i], 16)
+            assert np.abs(got - want).max() <= 1e-5 * max(1.0, np.abs(want).max())
