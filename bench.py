@@ -305,16 +305,20 @@ def cadence_bench(torch, rp, rpws, score_mode: str, device_index: int):
         torch.cuda.synchronize()
         w0 = bt.windows_scored()
         lat = []
+        stage = {}
         t0 = time.perf_counter()
         for _ in range(calls):
             t1 = time.perf_counter()
-            bt.process(host)
+            bt.process_count(host)
             lat.append((time.perf_counter() - t1) * 1e3)
+            for k, v in bt.last_timings().items():
+                stage[k] = stage.get(k, 0.0) + v / calls
         dt = time.perf_counter() - t0
         w = bt.windows_scored() - w0
         out[f"S{S}"] = {"streams": n, "calls": calls, "windows_per_s": round(w / dt, 1), "ms_per_call_median": round(float(np.median(lat)), 3),
                         "ms_per_call_p95": round(float(np.percentile(lat, 95)), 3), "launches_per_call": bt.last_launches(),
-                        "audio_ms_per_call": S / 16.0}
+                        "audio_ms_per_call": S / 16.0, "real_time_factor": round(S / 16.0 / float(np.median(lat)), 2),
+                        "stage_ms_per_call": {k: round(v, 3) for k, v in stage.items()}}
     del bt
     return out
 

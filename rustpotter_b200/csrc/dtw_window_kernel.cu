@@ -286,16 +286,19 @@ dtw_windows_d16_kernel(DtwWindowsArgs a, WindowLaunch L, const float* __restrict
                     G[t + NB - 1] = hsum(g);
                     A = -hsum(aa);                                     // a^_r . mu  (nmu is negated)
                 } else if (tid >= kNW) {
-                    // helper warp: the NB-1 lowest frames of this row's shared range
-#pragma unroll
-                    for (int e = tid - kNW; e < NB - 1; e += 32) {
-                        const int u = r - W - 1 + e;
+                    // helper warp: the NB-1 lowest frames of this row's shared range (a second pass only when NB-1 > 32)
+                    const int e0 = tid - kNW;
+                    if (e0 < NB - 1) {
+                        const int u = r - W - 1 + e0;
                         float g = 0.f;
-                        if (u >= 0) {
-                            const Row16 x = lds_row(Xs + u * kXS);
-                            g = dot16(ar, x);
-                        }
-                        G[e] = g;
+                        if (u >= 0) g = dot16(ar, lds_row(Xs + u * kXS));
+                        G[e0] = g;
+                    }
+                    if (NB - 1 > 32 && e0 + 32 < NB - 1) {
+                        const int u = r - W - 1 + e0 + 32;
+                        float g = 0.f;
+                        if (u >= 0) g = dot16(ar, lds_row(Xs + u * kXS));
+                        G[e0 + 32] = g;
                     }
                 }
                 __syncthreads();

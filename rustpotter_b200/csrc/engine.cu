@@ -67,7 +67,10 @@ Engine::Engine(int device, int64_t n_streams) : device_(device), n_streams_(n_st
     cuda_check(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking), "cudaStreamCreate");
     stream_ = own_stream_;
     cuda_check(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking), "cudaStreamCreate");
-    if (const char* g = std::getenv("RP_GROUP_STREAMS")) group_streams_ = std::max(1, std::atoi(g));
+    if (const char* g = std::getenv("RP_GROUP_STREAMS")) {
+        group_streams_ = std::max(1, std::atoi(g));
+        group_streams_fixed_ = true;
+    }
     for (auto& ev : ev_) cuda_check(cudaEventCreate(&ev), "cudaEventCreate");
     carry_.reserve((size_t)n_streams_ * 2 * kHopSamples * sizeof(float), "carry");
     cuda_check(cudaMemsetAsync(carry_.as<void>(), 0, carry_.bytes(), stream_), "memset carry");
@@ -287,7 +290,13 @@ void Engine::process(const AudioIn& in, bool want_vad, int first_window, std::ve
     // The batch is processed in groups of streams: group g's kernels wait only for group g's H2D copy,
     // so the copy of group g+1 (copy stream) overlaps the kernels of group g, and a group's frames
     // (~33 MB for 512 streams x 10 s) are still in L2 when its DTW kernel reads them.
-    const int64_t gs = std::min<int64_t>(group_streams_, n_streams_);
+    // (short calls — the reference's 30 ms cadence — take larger groups: at least ~16 MB of f32 audio per group, so that a
+    // chunk-by-chunk caller pays one launch chain per call instead of one per 256 streams)
+    int64_t gs = std::min<int64_t>(group_streams_, n_streams_);
+    if (!group_streams_fixed_) {
+        const int64_t min_streams = ((int64_t)16 << 20) / std::max<int64_t>(1, S * (int64_t)sizeof(float));
+        gs = std::min<int64_t>(n_streams_, std::max<int64_t>(gs, min_streams));
+    }
     const int n_groups = (int)((n_streams_ + gs - 1) / gs);
     while ((int)group_ev_.size() < 4 * n_groups) {
         cudaEvent_t ev;

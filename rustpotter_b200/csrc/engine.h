@@ -118,6 +118,7 @@ class Engine {
     cudaEvent_t ev_[6] = {};
     std::vector<cudaEvent_t> group_ev_;   // [group][4]: copy done, start, after MFCC, after DTW/judge
     int group_streams_ = 256;             // streams per pipeline group (RP_GROUP_STREAMS)
+    bool group_streams_fixed_ = false;    // set by RP_GROUP_STREAMS: no automatic enlargement for short calls
     int dtw_variant_ = 0;
     bool avg_gate_ = true;
 
