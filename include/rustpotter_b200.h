@@ -34,7 +34,7 @@ extern "C" {
 #define RP_ERR_INVALID (-1)     /* bad argument */
 #define RP_ERR_CUDA (-2)        /* no device / CUDA runtime failure */
 #define RP_ERR_FORMAT (-3)      /* not a WakewordRef / WakewordV2 CBOR file */
-#define RP_ERR_UNSUPPORTED (-4) /* outside this path (WakewordModel files, sample_rate != 16000, ...) */
+#define RP_ERR_UNSUPPORTED (-4) /* outside this path (WakewordModel files, ...) */
 #define RP_ERR_MISMATCH (-5)    /* wakewords with different mfcc_size (detector.rs:308-320) */
 
 #define RP_NAME_MAX 128
@@ -53,7 +53,7 @@ enum { RP_VAD_NONE = -1, RP_VAD_EASY = 0, RP_VAD_MEDIUM = 1, RP_VAD_HARD = 2 };
 /* RustpotterConfig { fmt: AudioFmt, detector: DetectorConfig, filters: FiltersConfig }
  * (src/config.rs:9-29,172-208,31-84,212-219), flattened. rp_config_default() = Default impls. */
 typedef struct rp_config {
-    uint32_t sample_rate;   /* 16000; other rates need the reference's rubato resampler: RP_ERR_UNSUPPORTED */
+    uint32_t sample_rate;   /* 16000; other rates go through the FFT resampler (encoder.rs:72-79) on the host first */
     uint32_t sample_format; /* RP_FMT_*; used by rp_process_bytes only */
     uint32_t channels;      /* channel 0 is used (encoder.rs:41-48) */
     uint32_t endianness;    /* RP_ENDIAN_* */
@@ -143,6 +143,10 @@ int rp_batch_create(const rp_config* cfg, int64_t n_streams, int device, rp_batc
  * per device drives its range inside every call. A multi-device batch takes HOST audio. */
 int rp_batch_create_multi(const rp_config* cfg, int64_t n_streams, const int* device_ids, int n_devices, rp_batch** out);
 int rp_batch_n_devices(const rp_batch* b);
+/* Rustpotter::get_samples_per_frame for one stream of the batch (480 * channels at 16 kHz; the resampler's input chunk * channels
+ * otherwise, e.g. 1440 at 48 kHz). With sample_rate != 16000 every stream is resampled on the host (one FftFixedInOut each) and
+ * the audio must be in host memory. */
+size_t rp_batch_samples_per_frame(const rp_batch* b);
 void rp_batch_destroy(rp_batch* b);
 int rp_batch_add_wakeword_from_buffer(rp_batch* b, const char* key, const uint8_t* buf, size_t len);
 int rp_batch_add_wakeword_from_file(rp_batch* b, const char* key, const char* path);
@@ -237,6 +241,10 @@ int rp_set_avg_gate(int mode);
 /* Selects the MFCC kernel: 0 = automatic (two-frames-per-warp TMA-staged kernel where it applies), 1 = one frame
  * per warp. For A/B measurements and parity tests. */
 int rp_set_mfcc_variant(int variant);
+/* The AudioEncoder's resampling stage on its own (encoder.rs:52-60: rubato FftFixedInOut, source rate -> 16 kHz, host code):
+ * whole input chunks of `in` (mono f32 at sample_rate_in) through a fresh resampler. Returns the number of output samples
+ * written (out may be NULL to query), or <0. *in_chunk (optional) receives the resampler's input chunk length. No GPU needed. */
+int64_t rp_resample_to_16k(uint32_t sample_rate_in, const float* in, size_t n_in, float* out, size_t out_cap, size_t* in_chunk);
 
 /* =============================================================================================
  * Host-logic hooks (no GPU needed): used by the CPU test-suite to exercise the wakeword-file

@@ -149,6 +149,8 @@ def lib(native: bool = False) -> C.CDLL:
     L.rpo_wakeword_build.argtypes = [C.c_char_p, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, C.POINTER(C.c_char_p),
                                      C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_char_p, C.c_size_t,
                                      C.c_char_p, C.c_size_t]
+    L.rpo_resample_to_16k.restype = C.c_int64
+    L.rpo_resample_to_16k.argtypes = [C.c_uint32, f32p, C.c_size_t, f32p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.rpo_detector_new.restype = C.c_void_p
     L.rpo_detector_new.argtypes = [C.POINTER(Config), C.c_char_p, C.c_size_t]
     L.rpo_detector_free.argtypes = [C.c_void_p]
@@ -408,6 +410,16 @@ class Detector:
 
     def windows_scored(self):
         return int(self._L.rpo_detector_windows_scored(self._h))
+
+
+def resample_to_16k(samples, sample_rate_in: int):
+    """rubato FftFixedInOut restated: mono f32 at sample_rate_in -> 16 kHz (whole chunks). Returns (out, input chunk)."""
+    a = _f32(samples)
+    chunk = C.c_size_t()
+    n = lib().rpo_resample_to_16k(sample_rate_in, _p(a), a.size, None, 0, C.byref(chunk))
+    out = np.zeros(n, np.float32)
+    lib().rpo_resample_to_16k(sample_rate_in, _p(a), a.size, _p(out), out.size, None)
+    return out, int(chunk.value)
 
 
 def trace_window_scores(config: Config, rpw: bytes, audio, n_templates: int) -> np.ndarray:

@@ -1395,6 +1395,20 @@ size_t rpo_wakeword_build(const char* name, int has_thr, float thr, int has_avg_
                                avg ? avg_flat.data() : nullptr, rms_level, has_thr, thr, has_avg_thr, avg_thr, 0, out, out_cap);
 }
 
+// The resampling stage alone (encoder.rs:52-60): whole chunks of mono f32 at fs_in -> 16 kHz through a fresh FftFixedInOut.
+int64_t rpo_resample_to_16k(uint32_t fs_in, const float* in, size_t n_in, float* out, size_t out_cap, size_t* in_chunk) {
+    FftFixedInOut r(fs_in, SAMPLE_RATE, SAMPLE_RATE * FRAME_LENGTH_MS / 1000);
+    if (in_chunk) *in_chunk = r.input_frames_next();
+    const size_t calls = n_in / r.fft_size_in;
+    if (!out) return (int64_t)(calls * r.fft_size_out);
+    if (calls * r.fft_size_out > out_cap) return -1;
+    for (size_t c = 0; c < calls; c++) {
+        Vec o = r.process(Vec(in + c * r.fft_size_in, in + (c + 1) * r.fft_size_in));
+        std::copy(o.begin(), o.end(), out + c * r.fft_size_out);
+    }
+    return (int64_t)(calls * r.fft_size_out);
+}
+
 rpo_detector* rpo_detector_new(const rpo_config* cfg, char* err, size_t err_len) {
     if (cfg->sample_rate == 0) { set_err(err, err_len, "bad sample rate"); return nullptr; }
     if (cfg->sample_format > 3 || cfg->channels == 0) { set_err(err, err_len, "bad audio format"); return nullptr; }

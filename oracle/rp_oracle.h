@@ -8,8 +8,8 @@
  * rustpotter_b200/ may include, link or call anything declared here.
  *
  * Parity status: PINNED — tests/test_oracle_golden.py checks this oracle against every
- * golden of the reference's tests/detector.rs that does not need the rubato resampler
- * (detector.rs:9-159) and against the template matrices stored in the reference's .rpw
+ * WakewordRef golden of the reference's tests/detector.rs (detector.rs:9-214, the two 48 kHz
+ * goldens through the restated rubato resampler included) and against the template matrices stored in the reference's .rpw
  * fixtures (which are the reference's own MFCC+CMN output for the fixture wavs).
  */
 #ifndef RP_ORACLE_H
@@ -121,6 +121,9 @@ size_t rpo_wakeword_build(const char* name, int has_thr, float thr, int has_avg_
 
 /* ---- Detector (src/detector.rs) ---- */
 typedef struct rpo_detector rpo_detector;
+/* rubato FftFixedInOut restated (source rate -> 16 kHz, one channel): whole input chunks through a fresh resampler.
+ * Returns output samples written (out may be NULL to query) or -1; *in_chunk = input chunk length. */
+int64_t rpo_resample_to_16k(uint32_t fs_in, const float* in, size_t n_in, float* out, size_t out_cap, size_t* in_chunk);
 rpo_detector* rpo_detector_new(const rpo_config* cfg, char* err, size_t err_len);
 void rpo_detector_free(rpo_detector*);
 int rpo_detector_add_wakeword_from_buffer(rpo_detector*, const char* key, const uint8_t* buf, size_t len,

@@ -85,7 +85,7 @@ EXPORTED = [
     "rp_batch_set_cuda_stream", "rp_batch_process", "rp_batch_update_config", "rp_batch_reset",
     "rp_batch_windows_scored", "rp_batch_n_streams", "rp_batch_max_mfcc_frames", "rp_batch_last_timings",
     "rp_batch_last_launches", "rp_batch_copy_last_scores", "rp_batch_create_multi", "rp_batch_n_devices",
-    "rp_batch_remove_wakeword", "rp_batch_process_samples", "rp_batch_process_bytes", "rp_batch_last_gate_stats", "rp_set_avg_gate", "rp_mfcc_frames", "rp_dtw_scores", "rp_set_dtw_variant", "rp_set_mfcc_variant", "rp_wakeword_inspect",
+    "rp_batch_remove_wakeword", "rp_batch_process_samples", "rp_batch_process_bytes", "rp_batch_last_gate_stats", "rp_set_avg_gate", "rp_batch_samples_per_frame", "rp_resample_to_16k", "rp_mfcc_frames", "rp_dtw_scores", "rp_set_dtw_variant", "rp_set_mfcc_variant", "rp_wakeword_inspect",
     "rp_wakeword_template", "rp_host_replay", "rp_wakeword_build", "rp_wakeword_from_features", "rp_debug_stream4_schedule", "rp_debug_stream4_ctl",
 ]
 
@@ -134,6 +134,10 @@ def lib() -> C.CDLL:
     L.rp_batch_process_bytes.argtypes = [vp, vp, C.c_int64, C.c_int, C.POINTER(C.POINTER(CBatchDetection)), C.POINTER(C.c_int64)]
     L.rp_batch_last_gate_stats.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.rp_set_avg_gate.argtypes = [C.c_int]
+    L.rp_batch_samples_per_frame.restype = C.c_size_t
+    L.rp_batch_samples_per_frame.argtypes = [vp]
+    L.rp_resample_to_16k.restype = C.c_int64
+    L.rp_resample_to_16k.argtypes = [C.c_uint32, f32p, C.c_size_t, f32p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.rp_batch_add_wakeword_from_buffer.argtypes = [vp, C.c_char_p, u8p, C.c_size_t]
     L.rp_batch_add_wakeword_from_file.argtypes = [vp, C.c_char_p, C.c_char_p]
     L.rp_batch_remove_wakewords.argtypes = [vp]
@@ -308,6 +312,9 @@ class RustpotterBatch:
     def n_devices(self) -> int:
         return self._L.rp_batch_n_devices(self._h)
 
+    def get_samples_per_frame(self) -> int:
+        return int(self._L.rp_batch_samples_per_frame(self._h))
+
     def set_cuda_stream(self, stream_handle: int):
         _check(self._L.rp_batch_set_cuda_stream(self._h, C.c_void_p(stream_handle)), self._h)
 
@@ -444,6 +451,18 @@ def set_dtw_variant(v: int):
 
 def set_mfcc_variant(v: int):
     lib().rp_set_mfcc_variant(v)
+
+
+def resample_to_16k(samples, sample_rate_in: int):
+    """The AudioEncoder's resampling stage alone (host code; rubato FftFixedInOut restated): mono f32 at sample_rate_in ->
+    16 kHz, whole chunks only. Returns (output float32 array, input chunk length)."""
+    a = np.ascontiguousarray(samples, np.float32)
+    chunk = C.c_size_t()
+    n = _check(int(lib().rp_resample_to_16k(sample_rate_in, a.ctypes.data_as(C.POINTER(C.c_float)), a.size, None, 0, C.byref(chunk))))
+    out = np.zeros(n, np.float32)
+    _check(int(lib().rp_resample_to_16k(sample_rate_in, a.ctypes.data_as(C.POINTER(C.c_float)), a.size,
+                                        out.ctypes.data_as(C.POINTER(C.c_float)), out.size, None)))
+    return out, int(chunk.value)
 
 
 def set_avg_gate(mode: int):

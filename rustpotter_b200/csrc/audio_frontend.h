@@ -12,6 +12,7 @@
 #include <optional>
 #include <vector>
 
+#include "resampler.h"
 #include "rp_internal.h"
 
 namespace rp {
@@ -19,6 +20,28 @@ namespace rp {
 struct AudioIngest {
     uint32_t fmt = RP_FMT_F32, channels = 1, endianness = RP_ENDIAN_LITTLE;
     size_t input_samples_per_frame = kFrameSamples;  // (sample_rate*30/1000) * channels (encoder.rs:68-69)
+    std::shared_ptr<FftResampler> resampler;         // encoder.rs:72-79: None when the source rate is 16 kHz
+    // AudioEncoder::new (encoder.rs:63-102)
+    void configure(const rp_config& c) {
+        fmt = c.sample_format;
+        channels = c.channels;
+        endianness = c.endianness;
+        input_samples_per_frame = (size_t)(c.sample_rate * 30 / 1000) * c.channels;
+        resampler.reset();
+        if (c.sample_rate != (uint32_t)kSampleRate) {
+            resampler = std::make_shared<FftResampler>(c.sample_rate, (size_t)kSampleRate, (size_t)kFrameSamples);
+            input_samples_per_frame = resampler->input_frames() * c.channels;
+        }
+    }
+    // samples per call that reach the MFCC extractor (480 without a resampler)
+    size_t output_samples_per_frame() const { return resampler ? resampler->output_frames() : (size_t)kFrameSamples; }
+    // reencode_to_mono_with_sample_rate (encoder.rs:41-62) after the channel pick
+    std::vector<float> finish(std::vector<float> mono) const {
+        if (!resampler) return mono;
+        std::vector<float> out(resampler->output_frames());
+        resampler->process(mono.data(), out.data());
+        return out;
+    }
     size_t bytes_per_sample() const { return fmt == RP_FMT_I8 ? 1 : fmt == RP_FMT_I16 ? 2 : 4; }
     size_t input_bytes_per_frame() const { return input_samples_per_frame * bytes_per_sample(); }
 
@@ -29,7 +52,9 @@ struct AudioIngest {
         for (size_t i = 0; i < n; i++) v[i] = v[i * channels];
         v.resize(n);
     }
-    std::vector<float> decode_bytes(const uint8_t* b, size_t len) const {
+    std::vector<float> decode_bytes(const uint8_t* b, size_t len) const { return finish(decode_bytes_mono(b, len)); }
+    // encode_audio_bytes + channel pick, before any resampling
+    std::vector<float> decode_bytes_mono(const uint8_t* b, size_t len) const {
         const size_t bs = bytes_per_sample();
         const bool big = endianness == RP_ENDIAN_BIG;  // native == little on the platforms this targets
         std::vector<float> out(len / bs);
@@ -51,7 +76,7 @@ struct AudioIngest {
         std::vector<float> out(n);
         for (size_t i = 0; i < n; i++) out[i] = max_value == 0.f ? (float)s[i] : (float)s[i] / max_value;
         to_mono(out);
-        return out;
+        return finish(std::move(out));
     }
 };
 

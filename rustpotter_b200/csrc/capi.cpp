@@ -59,6 +59,9 @@ struct rp_batch {
     std::vector<rp_batch_detection> dets;
     std::vector<std::vector<float>> stores;
     std::vector<float> timings = std::vector<float>(5, 0.f);
+    // source rate != 16 kHz (encoder.rs:72-79): one FftFixedInOut per stream, run on the host in front of the device path
+    std::vector<std::unique_ptr<FftResampler>> resamplers;
+    std::vector<float> resampled;   // [n_streams][calls * output_frames]
     DetectorCore& first() { return *shards.front().core; }
     const DetectorCore& first() const { return *shards.front().core; }
 };
@@ -99,7 +102,7 @@ int process_audio(rp_handle* h, std::vector<float> audio, rp_detection* out) {
     h->rms_level = GainNormalizer::rms_level(audio);
     if (h->gain_filter) h->gain = h->gain_filter->filter(audio, h->rms_level);
     if (h->band_pass) h->band_pass->filter(audio);
-    h->core->process(audio.data(), (int64_t)audio.size(), false, &h->gain, h->emitted);
+    h->core->process(audio.data(), (int64_t)audio.size(), false, &h->gain, h->emitted, (int)(audio.size() / (size_t)kHopSamples));
     if (h->emitted.empty()) return 0;
     if (out) h->core->fill_detection(h->emitted.front().det, out, h->score_store);
     return 1;
@@ -160,6 +163,35 @@ void for_each_shard(rp_batch* b, F&& f) {
 int batch_process(rp_batch* b, AudioIn in, const rp_batch_detection** dets, int64_t* n_dets) {
     if (b->shards.size() > 1 && in.on_device)
         throw Error(RP_ERR_INVALID, "a multi-device batch takes host audio (each device copies its own stream range)");
+    if (!b->resamplers.empty()) {   // reencode_to_mono_with_sample_rate for every stream, then the 16 kHz path
+        if (in.on_device) throw Error(RP_ERR_UNSUPPORTED, "resampling (sample_rate != 16000) takes host audio");
+        const size_t nin = b->resamplers.front()->input_frames(), nout = b->resamplers.front()->output_frames();
+        if (in.samples <= 0 || (size_t)in.samples % nin != 0)
+            throw Error(RP_ERR_INVALID, "samples_per_stream must be a multiple of the resampler's input chunk (rp_batch_samples_per_frame)");
+        const size_t calls = (size_t)in.samples / nin;
+        b->resampled.resize((size_t)b->n_streams * calls * nout);
+        AudioIngest dec;
+        dec.fmt = (uint32_t)in.fmt;
+        dec.channels = (uint32_t)in.channels;
+        dec.endianness = in.big_endian ? RP_ENDIAN_BIG : RP_ENDIAN_LITTLE;
+        const uint8_t* src = static_cast<const uint8_t*>(in.data);
+        const size_t sb = in.bytes_per_stream(), chunk_bytes = nin * (size_t)in.channels * in.bytes_per_sample();
+        const unsigned hw = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+        const unsigned nt = (unsigned)std::min<int64_t>(hw, b->n_streams);
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; t++)
+            th.emplace_back([&, t] {
+                for (int64_t s2 = t; s2 < b->n_streams; s2 += nt)
+                    for (size_t c = 0; c < calls; c++) {
+                        const std::vector<float> mono = dec.decode_bytes_mono(src + (size_t)s2 * sb + c * chunk_bytes, chunk_bytes);
+                        b->resamplers[(size_t)s2]->process(mono.data(), b->resampled.data() + ((size_t)s2 * calls + c) * nout);
+                    }
+            });
+        for (auto& t : th) t.join();
+        in = AudioIn();
+        in.data = b->resampled.data();
+        in.samples = (int64_t)(calls * nout);
+    }
     const size_t stream_bytes = in.bytes_per_stream();
     const uint8_t* base = static_cast<const uint8_t*>(in.data);
     const int gate = g_avg_gate.load();
@@ -245,10 +277,9 @@ int rp_create(const rp_config* cfg, int device, rp_handle** out) {
     return guarded((rp_handle*)nullptr, [&] {
         auto h = std::make_unique<rp_handle>();
         h->core = std::make_unique<DetectorCore>(*cfg, 1, device);
-        h->ingest.fmt = cfg->sample_format;
-        h->ingest.channels = cfg->channels;
-        h->ingest.endianness = cfg->endianness;
-        h->ingest.input_samples_per_frame = (size_t)(cfg->sample_rate * 30 / 1000) * cfg->channels;
+        h->ingest.configure(*cfg);   // AudioEncoder::new: sample decoding and, off 16 kHz, the FFT resampler
+        if (h->ingest.output_samples_per_frame() % (size_t)kHopSamples != 0)
+            throw Error(RP_ERR_UNSUPPORTED, "this source rate makes the resampler emit chunks that are not whole 10 ms hops");
         make_filters(h.get(), *cfg);
         *out = h.release();
         return RP_OK;
@@ -361,6 +392,13 @@ int rp_batch_create_multi(const rp_config* cfg, int64_t n_streams, const int* de
         auto b = std::make_unique<rp_batch>();
         b->n_streams = n_streams;
         b->cfg = *cfg;
+        if (cfg->sample_rate != (uint32_t)kSampleRate) {
+            for (int64_t i = 0; i < n_streams; i++)
+                b->resamplers.push_back(std::make_unique<FftResampler>(cfg->sample_rate, (size_t)kSampleRate, (size_t)kFrameSamples));
+            if (b->resamplers.front()->output_frames() != (size_t)kFrameSamples)
+                throw Error(RP_ERR_UNSUPPORTED, "the batched front-end needs a source rate whose resampler emits 480-sample chunks "
+                                                "(48000, 44100, 32000, 24000, 8000 ...)");
+        }
         for (int i = 0; i < n_devices; i++) {   // contiguous ranges [i*B/G, (i+1)*B/G)
             BatchShard sh;
             sh.begin = n_streams * i / n_devices;
@@ -380,6 +418,11 @@ int rp_batch_create(const rp_config* cfg, int64_t n_streams, int device, rp_batc
 }
 void rp_batch_destroy(rp_batch* b) { delete b; }
 int rp_batch_n_devices(const rp_batch* b) { return b ? (int)b->shards.size() : 0; }
+size_t rp_batch_samples_per_frame(const rp_batch* b) {   // get_samples_per_frame (detector.rs:204): one stream's 30 ms chunk
+    if (!b) return 0;
+    const size_t mono = b->resamplers.empty() ? (size_t)kFrameSamples : b->resamplers.front()->input_frames();
+    return mono * b->cfg.channels;
+}
 
 int rp_batch_add_wakeword_from_buffer(rp_batch* b, const char* key, const uint8_t* buf, size_t len) {
     if (!b || !key || !buf) return RP_ERR_INVALID;
@@ -438,8 +481,9 @@ int rp_batch_process_samples(rp_batch* b, const void* audio, int sample_format, 
     return guarded(b, [&] {
         if (sample_format < RP_FMT_I8 || sample_format > RP_FMT_F32) throw Error(RP_ERR_INVALID, "unknown sample format");
         const int64_t ch = (int64_t)b->cfg.channels;
-        if (samples_per_stream <= 0 || samples_per_stream % (kFrameSamples * ch) != 0)
-            throw Error(RP_ERR_INVALID, "samples_per_stream must be a positive multiple of 480 * channels");
+        const int64_t frame = (int64_t)rp_batch_samples_per_frame(b);
+        if (samples_per_stream <= 0 || samples_per_stream % frame != 0)
+            throw Error(RP_ERR_INVALID, "samples_per_stream must be a positive multiple of rp_batch_samples_per_frame()");
         AudioIn in;
         in.data = audio;
         in.fmt = sample_format;
@@ -459,7 +503,7 @@ int rp_batch_process_bytes(rp_batch* b, const uint8_t* bytes, int64_t bytes_per_
         in.fmt = (int)b->cfg.sample_format;
         in.channels = (int)b->cfg.channels;
         in.big_endian = b->cfg.endianness == RP_ENDIAN_BIG;
-        const int64_t frame_bytes = (int64_t)kFrameSamples * in.channels * (int64_t)in.bytes_per_sample();
+        const int64_t frame_bytes = (int64_t)rp_batch_samples_per_frame(b) * (int64_t)in.bytes_per_sample();
         if (bytes_per_stream <= 0 || bytes_per_stream % frame_bytes != 0)
             throw Error(RP_ERR_INVALID, "bytes_per_stream must be a positive multiple of rp_get_bytes_per_frame()");
         in.samples = bytes_per_stream / ((int64_t)in.channels * (int64_t)in.bytes_per_sample());
@@ -677,6 +721,23 @@ int rp_set_dtw_variant(int v) {
 int rp_set_mfcc_variant(int v) {
     set_mfcc_variant(v);
     return RP_OK;
+}
+
+int64_t rp_resample_to_16k(uint32_t sample_rate_in, const float* in, size_t n_in, float* out, size_t out_cap, size_t* in_chunk) {
+    int64_t written = 0;
+    const int rc = guarded((rp_handle*)nullptr, [&] {
+        if (sample_rate_in < 1000 || sample_rate_in > 768000 || (!in && n_in)) throw Error(RP_ERR_INVALID, "bad argument");
+        FftResampler r(sample_rate_in, (size_t)kSampleRate, (size_t)kFrameSamples);
+        if (in_chunk) *in_chunk = r.input_frames();
+        const size_t calls = n_in / r.input_frames();
+        written = (int64_t)(calls * r.output_frames());
+        if (out) {
+            if ((size_t)written > out_cap) throw Error(RP_ERR_INVALID, "output buffer too small");
+            for (size_t c = 0; c < calls; c++) r.process(in + c * r.input_frames(), out + c * r.output_frames());
+        }
+        return RP_OK;
+    });
+    return rc < 0 ? rc : written;
 }
 
 // ------------------------------------------------------------------ host-logic hooks

@@ -8,9 +8,8 @@
 namespace rp {
 
 DetectorCore::DetectorCore(const rp_config& cfg, int64_t n_streams, int device) : cfg_(cfg) {
-    if (cfg.sample_rate != (uint32_t)kSampleRate)
-        throw Error(RP_ERR_UNSUPPORTED,
-                    "sample_rate != 16000 needs the reference's rubato resampler, which is outside this path");
+    if (cfg.sample_rate < 1000 || cfg.sample_rate > 768000)
+        throw Error(RP_ERR_INVALID, "Unsupported sample rate, unable to initialize the resampler");   // encoder.rs:78
     if (cfg.sample_format > RP_FMT_F32 || cfg.channels == 0 || cfg.endianness > RP_ENDIAN_NATIVE)
         throw Error(RP_ERR_INVALID, "invalid configuration value");
     validate_detector_config(cfg);
@@ -110,11 +109,12 @@ uint64_t DetectorCore::windows_scored() const {
     return t;
 }
 
-void DetectorCore::process(const AudioIn& in, const float* gains, std::vector<Emitted>& out) {
+void DetectorCore::process(const AudioIn& in, const float* gains, std::vector<Emitted>& out, int chunk_hops) {
     out.clear();
     if (ws_.empty()) return;  // detector.rs:348-350: audio is dropped, extractor untouched
     const int64_t S = in.samples;
-    if (S <= 0 || S % kFrameSamples != 0) throw Error(RP_ERR_INVALID, "samples_per_stream must be a positive multiple of 480 per channel");
+    if (chunk_hops < 1 || S <= 0 || S % ((int64_t)kHopSamples * chunk_hops) != 0)
+        throw Error(RP_ERR_INVALID, "samples_per_stream must be a positive multiple of the chunk length (480 mono samples at 16 kHz)");
     if (!in.data || in.channels < 1 || in.fmt < RP_FMT_I8 || in.fmt > RP_FMT_F32) throw Error(RP_ERR_INVALID, "bad audio description");
     const bool vad = params_.vad_mode >= 0;
     // leading hops of this call that no stream can turn into a scored window (e.g. a freshly reset batch)
@@ -123,8 +123,8 @@ void DetectorCore::process(const AudioIn& in, const float* gains, std::vector<Em
     engine_->process(in, vad, (int)std::max<int64_t>(skip, 0), hits_, vad ? &vad_ : nullptr);
 
     const auto t0 = std::chrono::steady_clock::now();
-    const int64_t n_chunks = S / kFrameSamples;
-    const int64_t n_hops = n_chunks * kHopsPerChunk;
+    const int64_t n_hops = S / kHopSamples;
+    const int64_t n_chunks = n_hops / chunk_hops;
     const int64_t B = engine_->n_streams();
     const float* dev_gains = (device_filters_ && engine_->gain_filter_enabled()) ? engine_->last_gains().data() : nullptr;
     size_t hi = 0;
@@ -139,17 +139,17 @@ void DetectorCore::process(const AudioIn& in, const float* gains, std::vector<Em
         size_t hp = h0;
         for (int64_t c = 0; c < n_chunks;) {
             if (st.idle() && !vad) {  // jump to the chunk that holds the next judged detection
-                while (hp < hi && hits_[hp].frame < c * kHopsPerChunk) hp++;
-                const int64_t next = hp < hi ? hits_[hp].frame / kHopsPerChunk : n_chunks;
+                while (hp < hi && hits_[hp].frame < c * chunk_hops) hp++;
+                const int64_t next = hp < hi ? hits_[hp].frame / chunk_hops : n_chunks;
                 if (next > c) {
-                    st.skip_hops(params_, (next - c) * kHopsPerChunk);
+                    st.skip_hops(params_, (next - c) * chunk_hops);
                     c = next;
                     continue;
                 }
             }
             const float gain = gains ? gains[c] : (dev_gains ? dev_gains[(size_t)(b * n_chunks + c)] : 1.f);
-            for (int k = 0; k < kHopsPerChunk; k++) {
-                const int64_t j = c * kHopsPerChunk + k;
+            for (int k = 0; k < chunk_hops; k++) {
+                const int64_t j = c * chunk_hops + k;
                 while (hp < hi && hits_[hp].frame < j) hp++;
                 Hit hit;
                 const Hit* hptr = nullptr;

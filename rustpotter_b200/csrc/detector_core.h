@@ -34,13 +34,16 @@ class DetectorCore {
     void reset();                                       // :290-302
 
     // in.samples = n_chunks * 480 mono samples per stream; gains: per-chunk gain stamped on detections (nullptr = 1.0)
-    void process(const AudioIn& in, const float* gains, std::vector<Emitted>& out);
-    void process(const float* audio, int64_t samples_per_stream, bool on_device, const float* gains, std::vector<Emitted>& out) {
+    // chunk_hops: 10 ms hops that make up one caller-visible chunk (one process_samples call of the reference): 3 without
+    // a resampler; with one, whatever FftFixedInOut emits per call (a multiple of 160 samples is required here).
+    void process(const AudioIn& in, const float* gains, std::vector<Emitted>& out, int chunk_hops = kHopsPerChunk);
+    void process(const float* audio, int64_t samples_per_stream, bool on_device, const float* gains, std::vector<Emitted>& out,
+                 int chunk_hops = kHopsPerChunk) {
         AudioIn in;
         in.data = audio;
         in.samples = samples_per_stream;
         in.on_device = on_device;
-        process(in, gains, out);
+        process(in, gains, out, chunk_hops);
     }
 
     // Fills an rp_detection whose pointers refer to the detection's own name snapshot and to `score_store` (caller-owned).

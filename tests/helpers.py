@@ -135,3 +135,39 @@ def make_config5_wakewords(oracle, d=16):
         rpws.append(r)
         utts.append(u)
     return rpws, utts
+
+
+def read_wav_f32(path: str):
+    """Minimal RIFF reader for the reference's float fixtures (WAVE_FORMAT_EXTENSIBLE / IEEE float, which the `wave`
+    module rejects). Returns (sample_rate, channels, float32 samples)."""
+    import struct
+    f = open(path, "rb").read()
+    assert f[:4] == b"RIFF" and f[8:12] == b"WAVE"
+    p, rate, ch, data = 12, None, None, None
+    while p + 8 <= len(f):
+        cid, sz = f[p:p + 4], struct.unpack("<I", f[p + 4:p + 8])[0]
+        if cid == b"fmt ":
+            tag, ch, rate, _, _, bits = struct.unpack("<HHIIHH", f[p + 8:p + 24])
+            assert bits == 32 and tag in (3, 65534)
+        elif cid == b"data":
+            data = np.frombuffer(f[p + 8:p + 8 + sz], "<f4").copy()
+            break
+        p += 8 + sz + (sz & 1)
+    return rate, ch, data
+
+
+def real_sample_stream():
+    """tests/detector.rs:296-326 run_detection_with_audio_file input: real_sample.wav (48 kHz f32 mono) + 5 s of silence."""
+    rate, ch, x = read_wav_f32(golden("real_sample.wav"))
+    assert (rate, ch) == (48000, 1)
+    return rate, np.concatenate([x, np.zeros(rate * 5, np.float32)])
+
+
+# tests/detector.rs:162-214 — the reference's goldens on a 48 kHz recording (through its rubato resampler)
+REAL_SAMPLE_GOLDENS = [
+    (dict(avg_threshold=0.3, threshold=0.47, score_mode="max", min_scores=5),
+     [(0.4676845, 0.527971, 24), (0.32865646, 0.48120698, 7), (0.30807483, 0.5164661, 35)]),
+    (dict(avg_threshold=0.3, threshold=0.49, score_mode="max", min_scores=5, gain_normalizer_enabled=1, min_gain=0.4,
+          band_pass_enabled=1, low_cutoff=210.0, high_cutoff=700.0),
+     [(0.45496628, 0.5380342, 23), (0.336222, 0.5001262, 5), (0.3049497, 0.5189481, 31)]),
+]

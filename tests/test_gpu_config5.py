@@ -282,3 +282,47 @@ def test_multi_device_handle_matches_single_device():
         multi.process(torch.from_numpy(audio).cuda())      # device audio cannot be split by the library
     assert multi.remove_wakeword("w1") is True and one.remove_wakeword("w1") is True
     assert multi.max_mfcc_frames() == one.max_mfcc_frames()
+
+
+# ------------------------------------------------------------------ 48 kHz ingest
+@pytest.mark.parametrize("case", [0, 1], ids=["record_with_noise", "record_with_noise_using_filters"])
+def test_golden_48khz_record(case):
+    """tests/detector.rs:162-214 through the C ABI: a 48 kHz recording, resampled by the restated rubato FftFixedInOut on the
+    host, then the CUDA path. Counters exact, scores within the parity bar (observed ~1e-6)."""
+    from tests.helpers import REAL_SAMPLE_GOLDENS, real_sample_stream
+    kw, want = REAL_SAMPLE_GOLDENS[case]
+    rate, x = real_sample_stream()
+    det = rp.Rustpotter(rp.default_config(sample_rate=rate, sample_format="f32", channels=1, **kw))
+    det.add_wakeword_from_file("wakeword", golden("oye_casa_real.rpw"))
+    n = det.get_samples_per_frame()
+    assert n == 1440
+    got = [d for d in (det.process_samples(x[i:i + n]) for i in range(0, len(x) - n + 1, n)) if d is not None]
+    assert len(got) == len(want)
+    for d, (avg, score, counter) in zip(got, want):
+        assert d["counter"] == counter
+        assert _rel(d["avg_score"], avg) < SCORE_RTOL and _rel(d["score"], score) < SCORE_RTOL, (d, avg, score)
+
+
+def test_batch_48khz_streams_match_the_per_stream_handle():
+    """The batched front-end with sample_rate 48000: every stream through its own host resampler, then one device call."""
+    from tests.helpers import REAL_SAMPLE_GOLDENS, real_sample_stream
+    kw, want = REAL_SAMPLE_GOLDENS[0]
+    rate, x = real_sample_stream()
+    x = x[: x.size // 1440 * 1440]
+    shifted = np.concatenate([np.zeros(1440 * 7, np.float32), x[:-1440 * 7]])
+    audio = np.stack([x, shifted, (x * np.float32(0.5)).astype(np.float32)])
+    bt = rp.RustpotterBatch(3, rp.default_config(sample_rate=rate, **kw))
+    assert bt.get_samples_per_frame() == 1440
+    bt.add_wakeword_from_file("wakeword", golden("oye_casa_real.rpw"))
+    half = (x.size // 1440 // 2) * 1440
+    got = bt.process(audio[:, :half]) + [(s, c + half // 1440, d) for s, c, d in bt.process(audio[:, half:])]
+    per = {s: [d for s2, c, d in got if s2 == s] for s in range(3)}
+    assert [d["counter"] for d in per[0]] == [w[2] for w in want]
+    for d, (avg, score, counter) in zip(per[0], want):
+        assert _rel(d["score"], score) < SCORE_RTOL and _rel(d["avg_score"], avg) < SCORE_RTOL
+    assert len(per[1]) == 3 and len(per[2]) == 3
+    for a, b in zip(per[0], per[2]):   # a pure gain change leaves the cosine/CMN scores (nearly) unchanged
+        assert a["counter"] == b["counter"] and _rel(a["score"], b["score"]) < 1e-3
+    with pytest.raises(rp.RustpotterError):
+        import torch
+        bt.process(torch.zeros((3, 1440), device="cuda"))

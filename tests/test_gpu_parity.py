@@ -358,9 +358,11 @@ def test_api_error_behaviour():
     with pytest.raises(rp.RustpotterError):
         det.add_wakeword_from_buffer("bad", b"\x01\x02")
     assert det.remove_wakeword("nope") is False and det.remove_wakeword("w") is True and det.remove_wakewords() is False
-    with pytest.raises(rp.RustpotterError) as e:
-        rp.Rustpotter(rp.default_config(sample_rate=48000))               # resampler is out of scope
-    assert e.value.code == -4
+    d48 = rp.Rustpotter(rp.default_config(sample_rate=48000))             # FftFixedInOut: 1440 samples in, 480 out
+    assert d48.get_samples_per_frame() == 1440
+    assert rp.Rustpotter(rp.default_config(sample_rate=44100, channels=2)).get_samples_per_frame() == 2 * 1323
+    with pytest.raises(rp.RustpotterError):
+        rp.Rustpotter(rp.default_config(sample_rate=0))
     # stereo i32 big-endian bytes: channel 0 is used
     d2 = rp.Rustpotter(rp.default_config(sample_format="i32", channels=2, endianness="big"))
     assert d2.get_samples_per_frame() == 960 and d2.get_bytes_per_frame() == 3840

@@ -383,3 +383,48 @@ def test_cbor_reader_rejects_deep_nesting_without_recursing():
         with pytest.raises(rp.RustpotterError) as e:
             rp.wakeword_inspect(bytes([0xA1, 0x61, 0x78]) + bytes([byte]) * (1 << 20))
         assert e.value.code == -3
+
+
+@pytest.mark.parametrize("rate", [48000, 44100, 32000, 8000, 22050, 96000])
+def test_resampler_matches_oracle_and_a_float64_reference(rate):
+    """The product's host resampler (csrc/resampler.h, Stockham FFTs) against the oracle's restatement of rubato's
+    FftFixedInOut (recursive FFT) and against the same algorithm evaluated with numpy in float64."""
+    rng = np.random.default_rng(rate)
+    t = np.arange(rate) / rate
+    x = (0.4 * np.sin(2 * np.pi * 440.0 * t) + 0.2 * np.sin(2 * np.pi * 3100.0 * t + 1.0) + 0.05 * rng.standard_normal(rate)).astype(np.float32)
+    got, chunk = rp.resample_to_16k(x, rate)
+    want, chunk_o = O.resample_to_16k(x, rate)
+    assert chunk == chunk_o and got.shape == want.shape and got.size > 0
+    assert np.abs(got - want).max() < 3e-6
+    # float64 evaluation of the published algorithm
+    g = np.gcd(rate, 16000)
+    k = -(-480 // (16000 // g))
+    nin, nout = k * rate // g, k * 16000 // g
+    assert chunk == nin and got.size == (x.size // nin) * nout
+    n = np.arange(nin, dtype=np.float64)
+    w = (0.35875 - 0.48829 * np.cos(2 * np.pi * n / nin) + 0.14128 * np.cos(4 * np.pi * n / nin) - 0.01168 * np.cos(6 * np.pi * n / nin)) ** 2
+    rel = 1.0 / (1.0 + 42.08 / nin)
+    cutoff = rel * nout / nin if nin > nout else rel
+    y = w * np.sinc((n - nin // 2) * cutoff)
+    y /= y.sum()
+    ft = np.zeros(2 * nin)
+    ft[:nin] = y / (2 * nin)
+    F = np.fft.rfft(ft)
+    new_len = nin + 1 if nin < nout else nout
+    ref = np.zeros(got.size)
+    ov = np.zeros(nout)
+    for c in range(x.size // nin):
+        b = np.zeros(2 * nin)
+        b[:nin] = x[c * nin:(c + 1) * nin]
+        X = np.fft.rfft(b)
+        Y = np.zeros(nout + 1, complex)
+        Y[:new_len] = X[:new_len] * F[:new_len]
+        if new_len > nout:
+            Y[nout] = Y[nout].real
+        o = np.fft.irfft(Y, 2 * nout) * (2 * nout)
+        ref[c * nout:(c + 1) * nout] = o[:nout] + ov
+        ov = o[nout:]
+    assert np.abs(got - ref).max() < 5e-6
+    # a 440 Hz tone survives with its amplitude (unit passband gain)
+    mid = ref[nout:-nout]
+    assert 0.3 < np.abs(mid).max() < 0.8

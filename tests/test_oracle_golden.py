@@ -230,3 +230,26 @@ def test_bench_template_fixture_is_the_oracles_mfcc():
             got = z[f"w{w}_t{i}"]
             assert got.shape == want.shape == (CONFIG5_LENGTHS[w][i], 16)
             assert np.abs(got - want).max() <= 1e-5 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("case", [0, 1], ids=["record_with_noise", "record_with_noise_using_filters"])
+def test_golden_48khz_record_through_the_restated_resampler(case):
+    """tests/detector.rs:162-214: real_sample.wav is 48 kHz, so the reference feeds it through rubato's FftFixedInOut.
+    The oracle's restatement reproduces both goldens (scores, avg scores and counters) — the second golden was not used to
+    calibrate the restatement's cutoff."""
+    from tests.helpers import REAL_SAMPLE_GOLDENS, real_sample_stream
+    kw, want = REAL_SAMPLE_GOLDENS[case]
+    rate, x = real_sample_stream()
+    det = O.Detector(O.default_config(sample_rate=rate, sample_format="f32", channels=1, **kw))
+    det.add_wakeword_from_file("wakeword", golden("oye_casa_real.rpw"))
+    n = det.get_samples_per_frame()
+    assert n == 1440
+    got = []
+    for i in range(0, len(x) - n + 1, n):
+        d = det.process_samples(x[i:i + n])
+        if d is not None:
+            got.append(d)
+    assert len(got) == len(want)
+    for d, (avg, score, counter) in zip(got, want):
+        assert d["counter"] == counter
+        assert abs(float(d["avg_score"]) - avg) <= 2e-6 * avg and abs(float(d["score"]) - score) <= 2e-6 * score, (d, avg, score)
