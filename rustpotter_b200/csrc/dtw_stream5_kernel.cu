@@ -1,39 +1,38 @@
-// K2s v4 — streaming DTW scorer for INDEPENDENT (template, window) pairs, mfcc_size = 16, sm_100a.
+// K2s v5 — streaming DTW scorer for INDEPENDENT (template, window) pairs, mfcc_size = 16, sm_100a.
 //
 // Contract: reference src/mfcc/comparator.rs:18-26 over src/mfcc/dtw.rs:56-105 (banded DTW with the
 // asymmetric band [r-w, r+w-1], result cell D[m-1][n], cosine distance with similarity 0 for zero
 // vectors, cost/(m+n) -> logistic score).
 //
-// Same arithmetic as dtw_stream3_kernel.cu (a block of 8 window columns lives in registers as negated
-// unit vectors, the template streams past it two rows per step, FFMA2 dots with the DP chain of the
-// previous row interleaved), but the systolic array is turned by 90 degrees and the CTA is split in roles:
+// The consumer side is v4's (dtw_stream4_kernel.cu): a lane is one pair of a group of 32, four consumer warps own the
+// 8-column window blocks b = warp (mod 4) as a systolic array turned by 90 degrees, a block of negated unit columns lives
+// in registers (128 of them), the template streams past it two rows per step (128 FFMA2 with the DP chain of the previous
+// row interleaved), warp-uniform control words built on the host drive every step.
 //
-//  * CONSUMER warps 0..3: what v3 mapped to the five LANES of a pair is mapped to four WARPS, and a lane is
-//    one pair of a group of 32. Block index, band mask, block switches are warp-uniform and come from a
-//    host-built table of control words: no divergence, one straight-line step body of 277 instructions (128
-//    FFMA2; the band mask is applied with R2P + FSEL, measured faster than a second, mask-free body for the 15
-//    of a block's 24 steps that lie fully inside the band). All 32 lanes work (v3: 30); a warp whose block is outside the band skips the step
-//    instead of issuing masked work; the pipeline fill/drain of a group costs idle WARPS, which the second
-//    resident CTA fills, instead of idle issue slots. Cells issued per pair: 4656 (3810 useful), v3: 6144.
-//    Block b runs two steps behind block b-1, so one warp owns blocks b, b+4, b+8, .. back to back, boundary
-//    columns travel through a 4-deep exchange array in shared memory, and the consumers meet only every
-//    SECOND step ("super-step").
-//  * PRODUCER warps 4..7 (setmaxnreg hands their registers to the consumers: 56 vs 200): HBM -> registers ->
-//    unit length -> shared memory. Per super-step they fetch the template row pairs and the quarters of the
-//    next window block that a host-built static schedule (Stream4Sched, checked on the CPU by
-//    tests/test_host_logic.py) assigns to it, 32 bytes per thread, four threads per 128 contiguous bytes of
-//    one pair. No cp.async raw copy and no in-ring rewrite: shared-memory traffic is 53 KB per pair (v3: 81).
-//    Producers run up to two super-steps ahead of the consumers: four "full" and four "empty" named barriers
-//    (bar.arrive / bar.sync, 256 threads) order the ring slots, so a late HBM line stalls nobody.
-//  * A block switch is 32 conflict-free LDS.128 (the staged block is already negated and normalised).
+// What changed is how the data gets there. ncu on v4 (profiles/r02_ncu_k2s_raw.csv): its four PRODUCER warps execute 26 %
+// of all instructions (HBM -> registers -> unit length -> shared memory, on the same schedulers and the same FP32 pipe as
+// the consumers) and the consumers spend 21 % of their time at the full/empty barrier; the consumers' step body alone,
+// fed from shared memory with nothing else running, needs 633 cycles per step at this occupancy against 1383 in the
+// kernel (tools/microbench_k2s_ceiling.cu, profiles/r02_k2s_ceiling.txt). So:
+//  * ONE loader warp per CTA replaces the producers. Lane = pair: per unit of the host-built schedule (a template row
+//    pair or a quarter of a window block: 128 contiguous bytes of one pair) every lane issues one bulk async copy
+//    (cp.async.bulk.shared.global, the TMA path: UBLKCP in SASS) straight into the ring / staging slot; completion is
+//    counted in bytes on an mbarrier per batch (SYNCS.ARRIVE.TRANS64). No data passes through registers, ~10 instructions
+//    per unit and warp instead of ~160.
+//  * The RAW rows are normalised by the consumer that touches them first: the host-built control word says when a row
+//    load is the first read of that row by any warp (always block b_min(k) of row pair k); that warp scales the row to
+//    unit length in registers (it needs it there anyway) and writes it back, every later reader — at least one
+//    super-step barrier away — finds unit rows. 26 instructions per template row per group. Staged window blocks are
+//    normalised (and negated) when a warp switches to them, as v4 did for its first block.
+//  * The consumers meet at their own 128-thread barrier per super-step (boundary columns), wait for the batch's mbarrier,
+//    and release ring slots to the loader through the named "empty" barriers as before.
 //
-// Shapes: d == 16, uniform m >= 2, n >= 1, no CMN, 3 <= window = max(band, |m-n|) <= 20, at most 238 steps.
-// Everything else takes the older kernels. Measured (B200, 1 M pairs 120x16 / 100x16): 6.46 ms = 2.18 TB/s algorithmic;
-// what bounds it (FP32 issue, two consumer warps per scheduler) and the variants that were measured and dropped are in
-// DESIGN.md section 6 and profiles/r01_SUMMARY.md.
+// Shapes: d == 16, uniform m >= 2, n >= 1, no CMN, 3 <= window = max(band, |m-n|) <= 20, at most 238 steps, 16-byte
+// aligned pair offsets. Everything else takes the older kernels.
 #include <cfloat>
 #include <cmath>
 #include <algorithm>
+#include <cstdint>
 #include <cstring>
 
 #include "kernels.h"
@@ -44,7 +43,7 @@ namespace {
 constexpr int kD = 16;
 constexpr int CB = 8;                                 // window columns per block
 constexpr int NW = 4;                                 // consumer warps per CTA = blocks of one pair in flight
-constexpr int NTHREADS = 2 * NW * 32;                 // + as many producer threads
+constexpr int NTHREADS = NW * 32 + 32;                // + one loader warp
 constexpr int PPG = 32;                               // pairs per group (one per lane)
 constexpr int SIGMA = 2;                              // block b runs SIGMA steps behind block b-1
 constexpr int PITCH = 4 + SIGMA;                      // steps between the starts of consecutive blocks
@@ -57,10 +56,11 @@ constexpr int RING_F = PPG * RING_PAIR_F;
 constexpr int STAGE_F = PPG * STAGE_PAIR_F;
 constexpr int XCH_F = NW * XS * 2 * 32;
 constexpr int XDRAIN_F = NW * 32;                     // one more value per warp and pair: the last row of a finished block
-constexpr int SMEM_FLOATS = RING_F + STAGE_F + XCH_F + XDRAIN_F;
-constexpr int SMEM_BYTES = SMEM_FLOATS * 4;           // 103,936 bytes: two CTAs per SM
+constexpr int MBAR_F = 8;                             // four 8-byte mbarriers ("batch landed")
+constexpr int SMEM_FLOATS = RING_F + STAGE_F + XCH_F + XDRAIN_F + MBAR_F;
+constexpr int SMEM_BYTES = SMEM_FLOATS * 4;           // ~104 KB: two CTAs per SM
 constexpr int MIN_WINDOW = 3, MAX_WINDOW = 20;
-constexpr int CONSUMER_REGS = 200, PRODUCER_REGS = 56;
+constexpr int CONSUMER_REGS = 200, LOADER_REGS = 40;
 constexpr int DEPTH = 2;                              // super-steps the producers may run ahead of the consumers
 constexpr int BAR_FULL = 1, BAR_EMPTY = 5, BAR_CONSUMERS = 9, BAR_GROUP = 10;   // named barriers 1..4 (full), 5..8 (empty)
 
@@ -92,11 +92,29 @@ __device__ __forceinline__ float min3(float a, float b, float c) {
     return d;
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-// 32 bytes of a stream that is read exactly once
-__device__ __forceinline__ void ldg32(const float* p, ulonglong2& v0, ulonglong2& v1) {
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v0.x), "=l"(v0.y) : "l"(p));
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2+16];" : "=l"(v1.x), "=l"(v1.y) : "l"(p));
+// ---- mbarrier / bulk-copy (TMA) primitives; shared-memory addresses are 32-bit shared::cta addresses
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {   // one arrival + the bytes the batch will deliver
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// global -> shared bulk async copy (TMA, UBLKCP): bytes is a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// orders this thread's generic-proxy accesses to shared memory before later async-proxy (bulk copy) writes of the same bytes
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NTHREADS) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(NTHREADS) : "memory"); }
 
@@ -133,19 +151,22 @@ __device__ __forceinline__ void load_block_global(const float* __restrict__ win,
     }
 }
 
-// The staged copy of a block is already negated and of unit length.
+// The staged copy of a block is raw (bulk-copied): negate and scale to unit length while loading.
 __device__ __forceinline__ void load_block_staged(const float* __restrict__ stage, f2 (&bcol)[CB][8]) {
 #pragma unroll
-    for (int j = 0; j < CB; j++)
+    for (int j = 0; j < CB; j++) {
+        f2 x[8];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(stage + j * kD + 4 * q);
-            bcol[j][2 * q] = v.x;
-            bcol[j][2 * q + 1] = v.y;
+            x[2 * q] = v.x;
+            x[2 * q + 1] = v.y;
         }
+        unit_column(x, bcol[j]);
+    }
 }
 
-// Reads one 64-byte (already unit-length) template row from the ring.
+// Reads one 64-byte template row from the ring.
 __device__ __forceinline__ void load_row(const float* __restrict__ p, f2 (&ar)[8]) {
 #pragma unroll
     for (int q = 0; q < 4; q++) {
@@ -165,23 +186,23 @@ __device__ __forceinline__ void load_row_if(const float* __restrict__ p, f2 (&ar
                      : "r"(sa + 16 * q), "r"((int)pred));
 }
 
-// Half a 64-byte vector (v0, v1) -> scaled by sign / |vector| (the partner lane holds the other half; a zero
-// vector stays zero: similarity 0, distance 1) -> shared memory.
-__device__ __forceinline__ void norm_store(const ulonglong2& v0, const ulonglong2& v1, float* __restrict__ dst, float sign, bool store) {
-    const f2 s = fma2(v1.y, v1.y, fma2(v1.x, v1.x, fma2(v0.y, v0.y, mul2(v0.x, v0.x))));
-    const float part = hsum(s);
-    const float nn = part + __shfl_xor_sync(0xffffffffu, part, 1);
-    const float sc = nn > 0.f ? sign * rsqrtf(nn) : 0.f;
-    const f2 s2 = pk(sc, sc);
-    ulonglong2 o0, o1;
-    o0.x = mul2(v0.x, s2);
-    o0.y = mul2(v0.y, s2);
-    o1.x = mul2(v1.x, s2);
-    o1.y = mul2(v1.y, s2);
-    if (store) {
-        *reinterpret_cast<ulonglong2*>(dst) = o0;
-        *reinterpret_cast<ulonglong2*>(dst + 4) = o1;
+// A raw 64-byte template row in registers -> unit length (a zero row stays zero: similarity 0, distance 1) and back to
+// the ring, for every later reader. Done by the warp whose load is the first read of that row (CTL_NORM_*).
+__device__ __forceinline__ void unit_row_store(f2 (&ar)[8], float* __restrict__ p) {
+    f2 n2 = mul2(ar[0], ar[0]);
+    f2 n3 = mul2(ar[1], ar[1]);
+#pragma unroll
+    for (int q = 2; q < 8; q += 2) {
+        n2 = fma2(ar[q], ar[q], n2);
+        n3 = fma2(ar[q + 1], ar[q + 1], n3);
     }
+    const float nn = hsum(n2) + hsum(n3);
+    const float sc = nn > 0.f ? rsqrtf(nn) : 0.f;
+    const f2 s2 = pk(sc, sc);
+#pragma unroll
+    for (int q = 0; q < 8; q++) ar[q] = mul2(ar[q], s2);
+#pragma unroll
+    for (int q = 0; q < 4; q++) *reinterpret_cast<ulonglong2*>(p + 4 * q) = make_ulonglong2(ar[2 * q], ar[2 * q + 1]);
 }
 
 // One half-step: the dots of template row `ar` with the block's eight columns (acc), interleaved with the
@@ -206,13 +227,14 @@ __device__ __forceinline__ void half_step(const f2 (&ar)[8], const f2 (&bcol)[CB
 
 // One step of a block: template rows 2u-1 and 2u (rp0 = ring slot of row pair u, rp1 = of u+1) against the eight columns.
 // full: every cell is inside the band (warp-uniform); otherwise M masks the costs (bits 7-j: row 2u-1, 8-j: row 2u).
-__device__ __forceinline__ void block_step(const float* __restrict__ rp0, const float* __restrict__ rp1, bool full, unsigned M, float li1,
+__device__ __forceinline__ void block_step(float* __restrict__ rp0, float* __restrict__ rp1, bool norm_a, bool norm_b, bool full, unsigned M, float li1,
                                            float li2p, float li1_prev, const f2 (&bcol)[CB][8], f2 (&ar1)[8], float (&D1)[CB],
                                            float (&D2)[CB], float (&cost2)[CB], float& out1, float& out2, f2 one) {
     f2 ar2[8], acc[CB];
     float cost1[CB];
     // ---- H1: dots of row 2u-1, DP of row 2u-2
     load_row(rp0 + kD, ar2);
+    if (norm_a) unit_row_store(ar2, rp0 + kD);   // first read of row 2u by any warp (warp-uniform)
     half_step(ar1, bcol, acc, cost2, D1, D2, li2p, li1_prev, one);
     out2 = D2[CB - 1];
 #pragma unroll
@@ -224,6 +246,7 @@ __device__ __forceinline__ void block_step(const float* __restrict__ rp0, const 
     }
     // ---- H2: dots of row 2u, DP of row 2u-1
     load_row(rp1, ar1);
+    if (norm_b) unit_row_store(ar1, rp1);        // first read of row 2u+1 (look-ahead for the next step)
     half_step(ar2, bcol, acc, cost1, D2, D1, li1, li2p, one);
     out1 = D1[CB - 1];
 #pragma unroll
@@ -269,10 +292,15 @@ constexpr unsigned CTL_HAS_LEFT = 1u << 8;      // block > 0
 constexpr unsigned CTL_NEXT_EXISTS = 1u << 9;   // (switch steps) block + 4 exists
 constexpr unsigned CTL_NEXT_PARITY = 1u << 10;  // (switch steps) its staging slot
 constexpr unsigned CTL_NEXT_LAST = 1u << 11;    // (switch steps) it is the pair's last block
+constexpr unsigned CTL_NORM_A = 1u << 26;       // row 2u (loaded in H1) is read here for the first time: scale to unit length, write back
+constexpr unsigned CTL_NORM_B = 1u << 27;       // the same for the look-ahead row 2u+1 (loaded in H2)
+constexpr unsigned CTL_NORM_F = 1u << 28;       // the same for row 2u-1 loaded by a fresh block
 constexpr int CTL_MASK_SHIFT = 12;              // 10 bits: band mask
 constexpr int CTL_SLOT_SHIFT = 22;              // 4 bits: row pair u & 15
 
 __device__ __forceinline__ void consumer_loop(const DtwPairsArgs& a, int64_t n_groups, const Geometry& g, float* smem, const Stream4Sched& sched) {
+    const unsigned full_bar = (unsigned)__cvta_generic_to_shared(smem + RING_F + STAGE_F + XCH_F + XDRAIN_F);   // four mbarriers
+    unsigned batch0 = 0;   // running number of the group's first batch (the loader counts the same way)
     const int lane = threadIdx.x & 31;
     const int wid = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform, 0..3
     const int m = g.m, n = g.n, n_blocks = g.n_blocks, steps = g.steps;
@@ -288,7 +316,7 @@ __device__ __forceinline__ void consumer_loop(const DtwPairsArgs& a, int64_t n_g
     unsigned dr_o = (unsigned)((RING_F + STAGE_F + XCH_F + left_w * 32 + lane) * 4);
     asm volatile("" : "+r"(ring_o), "+r"(stage_o), "+r"(xw_o), "+r"(xr_o), "+r"(dw_o), "+r"(dr_o));
     char* const sm = reinterpret_cast<char*>(smem);
-    const float* const ring_p = reinterpret_cast<const float*>(sm + ring_o);
+    float* const ring_p = reinterpret_cast<float*>(sm + ring_o);
     const float* const stage_p = reinterpret_cast<const float*>(sm + stage_o);
     float* const xch_w = reinterpret_cast<float*>(sm + xw_o);
     const float* const xch_r = reinterpret_cast<const float*>(sm + xr_o);
@@ -301,7 +329,7 @@ __device__ __forceinline__ void consumer_loop(const DtwPairsArgs& a, int64_t n_g
         const int64_t pc = valid ? p : a.n_pairs - 1;                       // clamped: every lane computes on real data
         const float* const win = a.win + (a.win_off ? a.win_off[pc] : pc * (int64_t)n * kD);
 
-        // ---- super-step 0: the warp's first block straight from global memory (the producers fill the ring meanwhile)
+        // ---- super-step 0: the warp's first block straight from global memory (the loader's first batches are in flight)
         bool on_last = wid == n_blocks - 1;
         f2 bcol[CB][8];
         if (wid < n_blocks) {
@@ -330,7 +358,12 @@ __device__ __forceinline__ void consumer_loop(const DtwPairsArgs& a, int64_t n_g
 
         unsigned ctl_next = sched.ctl[wid][1];
         for (int S = 1; S <= g.n_super; S++) {
-            bar_sync(BAR_FULL + ((S - 1) & 3));   // batch S-1 of the producers, and the neighbours' boundary values
+            {   // batch S-1 has landed (bulk copies count their bytes on its mbarrier) ...
+                const unsigned t = batch0 + (unsigned)(S - 1);
+                mbar_wait(full_bar + 8u * (t & 3u), (t >> 2) & 1u);
+            }
+            // ... and the neighbours' boundary values and first-touch rows of the last super-step are written
+            asm volatile("bar.sync %0, %1;" ::"n"(BAR_CONSUMERS), "n"(NW * 32) : "memory");
 #pragma unroll 1
             for (int st = 2 * S - 1; st <= min(2 * S, steps); st++) {
                 const unsigned ctl = ctl_next;
@@ -339,10 +372,11 @@ __device__ __forceinline__ void consumer_loop(const DtwPairsArgs& a, int64_t n_g
                 const unsigned so = ((ctl >> CTL_SLOT_SHIFT) & 15u) * (SLOT_F * 4);   // byte offset of row pair u in the ring
                 const unsigned so1 = (so + SLOT_F * 4) & (SLOTS * SLOT_F * 4 - 1);      // ... of row pair u+1
                 const unsigned xo = ((ctl >> CTL_SLOT_SHIFT) & 3u) * 256;               // ... of row pair u in the exchange array
-                const float* const rp0 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(ring_p) + so);
-                const float* const rp1 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(ring_p) + so1);
+                float* const rp0 = reinterpret_cast<float*>(reinterpret_cast<char*>(ring_p) + so);
+                float* const rp1 = reinterpret_cast<float*>(reinterpret_cast<char*>(ring_p) + so1);
                 // fresh block: no look-ahead happened, and the step before it was skipped
                 load_row_if(rp0, ar1, (ctl & CTL_FRESH) != 0);
+                if (ctl & CTL_NORM_F) unit_row_store(ar1, rp0);   // (first read of row 2u-1 by any warp)
                 ok2_prev = (ctl & CTL_FRESH) ? (ctl & CTL_OK2PREV) != 0 : ok2_prev;
                 // D[2u-2][c0-1]: the left block's H1 of row pair u, or its drain if row pair u-1 was its last (block 0 reads
                 // the last warp's values and ignores them)
@@ -352,8 +386,8 @@ __device__ __forceinline__ void consumer_loop(const DtwPairsArgs& a, int64_t n_g
                 const float li2p = ok2_prev ? shf2 : dseed;              // left input of row 2u-2 = diagonal input of row 2u-1
                 const float li1 = (ctl & CTL_OK1) ? shf1 : INFINITY;     // left input of row 2u-1 = diagonal input of row 2u
                 dseed = INFINITY;
-                block_step(rp0, rp1, (ctl & CTL_FULL) != 0, (ctl >> CTL_MASK_SHIFT) & 0x3ffu, li1, li2p, li1_prev, bcol, ar1, D1, D2, cost2,
-                           out1, out2, one);
+                block_step(rp0, rp1, (ctl & CTL_NORM_A) != 0, (ctl & CTL_NORM_B) != 0, (ctl & CTL_FULL) != 0, (ctl >> CTL_MASK_SHIFT) & 0x3ffu, li1,
+                           li2p, li1_prev, bcol, ar1, D1, D2, cost2, out1, out2, one);
                 li1_prev = li1;
                 ok2_prev = (ctl & CTL_OK2) != 0;
                 {
@@ -373,7 +407,7 @@ __device__ __forceinline__ void consumer_loop(const DtwPairsArgs& a, int64_t n_g
                         }
                         xdrain_w[0] = left;
                     }
-                    // the warp's next block, already staged (negated, unit length)
+                    // the warp's next block from its staging slot (raw; negated and scaled to unit length on the way)
                     if (ctl & CTL_NEXT_EXISTS) load_block_staged(stage_p + ((ctl & CTL_NEXT_PARITY) ? CB * kD : 0), bcol);
                     on_last = (ctl & CTL_NEXT_LAST) != 0;
 #pragma unroll
@@ -386,12 +420,15 @@ __device__ __forceinline__ void consumer_loop(const DtwPairsArgs& a, int64_t n_g
                     ok2_prev = false;
                 }
             }
-            // this super-step's ring and stage reads are over (batch S+DEPTH waits for it, if there is one)
+            // this super-step's ring and stage accesses are over (batch S+DEPTH waits for it, if there is one); the rows this
+            // thread wrote back must be ordered before the bulk copies that will overwrite their slots
+            fence_proxy_async();
             if (S <= g.n_super - 1 - DEPTH) bar_arrive(BAR_EMPTY + (S & 3));
         }
+        batch0 += (unsigned)g.n_super;
 
         // ---- result: the warp that owns the last block
-        // the group's reads of the ring are over: the producers may store the next group's first batches
+        // the group's accesses to the ring are over: the loader may start the next group's first batches
         if (grp + gridDim.x < n_groups) bar_arrive(BAR_GROUP);
         // the drain of the last row needs the left neighbour's last values: one more consumer-only rendezvous
         asm volatile("bar.sync %0, %1;" ::"n"(BAR_CONSUMERS), "n"(NW * 32) : "memory");
@@ -426,83 +463,77 @@ __device__ __forceinline__ void consumer_loop(const DtwPairsArgs& a, int64_t n_g
     }
 }
 
-// ------------------------------------------------------------------------------------------------ producers
+// ------------------------------------------------------------------------------------------------ loader
 // Unit codes of the schedule: 0 nothing; 1 .. kmax: template row pair k; 0x8000 | (B << 2) | j: quarter j of window block B.
-__device__ __forceinline__ void producer_loop(const DtwPairsArgs& a, int64_t n_groups, const Geometry& g, float* smem, const Stream4Sched& sched) {
-    const int tid = threadIdx.x - NW * 32;               // 0..127
-    const int fp = tid >> 2, part = tid & 3;              // 32-byte part `part` of pair `fp`'s 128-byte unit
-    const int my_row = part >> 1;                         // rows: (half of) row 2k-1+my_row; quarters: column 2j+my_row
-    const int m = g.m, n = g.n, n_blocks = g.n_blocks;
-    float* const ring_f = smem + fp * RING_PAIR_F + part * 8;
-    float* const stage_f = smem + RING_F + fp * STAGE_PAIR_F + my_row * kD + (part & 1) * 8;
+// Lane = pair: every unit is 128 contiguous bytes of the lane's pair in global memory and in its ring / staging slot.
+__device__ __forceinline__ void loader_loop(const DtwPairsArgs& a, int64_t n_groups, const Geometry& g, float* smem, const Stream4Sched& sched) {
+    const int lane = threadIdx.x & 31;
+    const int m = g.m, n = g.n;
+    const unsigned smem_a = (unsigned)__cvta_generic_to_shared(smem);
+    const unsigned ring_a = smem_a + (unsigned)(lane * RING_PAIR_F * 4);
+    const unsigned stage_a = smem_a + (unsigned)((RING_F + lane * STAGE_PAIR_F) * 4);
+    const unsigned full_bar = smem_a + (unsigned)((RING_F + STAGE_F + XCH_F + XDRAIN_F) * 4);
+    unsigned batch = 0;   // running batch number: mbarrier (batch & 3), phase parity (batch >> 2) & 1
 
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-        const int64_t pf = min(grp * PPG + fp, a.n_pairs - 1);
-        const float* const winf = a.win + (a.win_off ? a.win_off[pf] : pf * (int64_t)n * kD);
-        const float* const tmplf = a.tmpl + (a.tmpl_off ? a.tmpl_off[pf] : pf * (int64_t)m * kD);
-        {   // L2: rows and the window block the first batches fetch, and the head of this CTA's next group
-            if (2 * (part + 1) - 1 <= m) prefetch_l2(tmplf + (size_t)(2 * part) * kD);
-            if (2 * (part + 5) - 1 <= m) prefetch_l2(tmplf + (size_t)(2 * (part + 4)) * kD);
-            if (NW < n_blocks) prefetch_l2(winf + (size_t)min(NW * CB + 2 * part, n - 1) * kD);
-            const int64_t gn = grp + gridDim.x;
-            if (gn < n_groups && !a.win_off && !a.tmpl_off) {
-                const int64_t pn = min(gn * PPG + fp, a.n_pairs - 1);
-                const float* wn = a.win + pn * (int64_t)n * kD;
-                const float* tn = a.tmpl + pn * (int64_t)m * kD;
-                if (2 * part + 1 <= m) prefetch_l2(tn + (size_t)(2 * part) * kD);
-#pragma unroll
-                for (int b = 0; b < NW; b++) prefetch_l2(wn + (size_t)min(b * CB + 2 * part, n - 1) * kD);
-            }
-        }
-        for (int c = 0; c < g.n_super; c++) {
-            // batch c: what the consumers first read in super-step c+1.
-            // All loads first (they need no shared memory), then the wait for the ring slots, then scale and store.
-            ulonglong2 v[4][2];
-            float* dst[4];
-            float sign[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const unsigned un = sched.unit[c][i];
-                v[i][0] = make_ulonglong2(0ull, 0ull);
-                v[i][1] = v[i][0];
-                dst[i] = nullptr;
-                sign[i] = 1.f;
-                if (un & 0x8000u) {
-                    const int Bq = (un & 0x7fffu) >> 2, j = un & 3u;
-                    const int col = min(Bq * CB + 2 * j + my_row, n - 1);
-                    ldg32(winf + (size_t)col * kD + (part & 1) * 8, v[i][0], v[i][1]);
-                    if (part == 0 && Bq + 1 < n_blocks) prefetch_l2(winf + (size_t)min((Bq + 1) * CB + 2 * j, n - 1) * kD);
-                    dst[i] = stage_f + (Bq & 1) * (CB * kD) + 2 * j * kD;
-                    sign[i] = -1.f;
-                } else if (un) {
-                    const int k = (int)un;
-                    const float* src = tmplf + (size_t)(2 * k - 2) * kD + part * 8;
-                    if (2 * k - 1 + my_row <= m) ldg32(src, v[i][0], v[i][1]);
-                    if (part == 0 && 2 * (k + 8) - 1 <= m) prefetch_l2(src + 8 * SLOT_F);
-                    dst[i] = ring_f + (k & (SLOTS - 1)) * SLOT_F;
-                }
-            }
-            // the slots this batch overwrites were last read in super-step c-DEPTH at the latest (Stream4Sched invariant),
+        const int64_t pf = min(grp * PPG + lane, a.n_pairs - 1);
+        const float* const winf = a.win + pf * (int64_t)n * kD;
+        const float* const tmplf = a.tmpl + pf * (int64_t)m * kD;
+        for (int c = 0; c < g.n_super; c++, batch++) {
+            // the slots this batch overwrites were last touched in super-step c-DEPTH at the latest (Stream4Sched invariant),
             // or by the previous group
             if (c >= DEPTH) bar_sync(BAR_EMPTY + ((c - DEPTH) & 3));
             else if (c == 0 && grp != (int64_t)blockIdx.x) bar_sync(BAR_GROUP);
+            const float* src[4];
+            unsigned dst[4], bytes[4], total = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const unsigned un = sched.unit[c][i];
+                src[i] = nullptr;
+                dst[i] = 0;
+                bytes[i] = 0;
+                if (un & 0x8000u) {   // two window columns (a quarter block); columns >= n are not copied (their cells are never read)
+                    const int Bq = (un & 0x7fffu) >> 2, j = un & 3u;
+                    const int c0 = Bq * CB + 2 * j;
+                    const int valid = min(max(n - c0, 0), 2);
+                    src[i] = winf + (size_t)c0 * kD;
+                    dst[i] = stage_a + (unsigned)(((Bq & 1) * (CB * kD) + 2 * j * kD) * 4);
+                    bytes[i] = (unsigned)valid * (kD * 4);
+                } else if (un) {      // template rows 2k-1, 2k (the second one only if it exists)
+                    const int k = (int)un;
+                    src[i] = tmplf + (size_t)(2 * k - 2) * kD;
+                    dst[i] = ring_a + (unsigned)((k & (SLOTS - 1)) * SLOT_F * 4);
+                    bytes[i] = (unsigned)min(max(m - (2 * k - 2), 0), 2) * (kD * 4);
+                }
+                total += bytes[i];
+            }
+            const unsigned bar = full_bar + 8u * (batch & 3u);
+            if (lane == 0) mbar_expect_tx(bar, total * 32u);   // (an empty batch is a plain arrival: its phase still completes)
+            __syncwarp();
 #pragma unroll
             for (int i = 0; i < 4; i++)
-                if (sched.unit[c][i]) norm_store(v[i][0], v[i][1], dst[i], sign[i], true);   // uniform; the shuffle inside needs every lane
-            __threadfence_block();
-            bar_arrive(BAR_FULL + (c & 3));
+                if (bytes[i]) bulk_g2s(dst[i], src[i], bytes[i], bar);
         }
     }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 2) dtw_pairs_stream4_kernel(DtwPairsArgs a, int64_t n_groups, int window, Stream4Sched sched) {
+__global__ void __launch_bounds__(NTHREADS, 2) dtw_pairs_stream5_kernel(DtwPairsArgs a, int64_t n_groups, int window, Stream4Sched sched) {
     extern __shared__ __align__(16) float smem[];
     for (int i = threadIdx.x; i < SMEM_FLOATS; i += NTHREADS) smem[i] = 0.f;
     __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned full_bar = (unsigned)__cvta_generic_to_shared(smem + RING_F + STAGE_F + XCH_F + XDRAIN_F);
+        for (unsigned i = 0; i < 4; i++) mbar_init(full_bar + 8u * i, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_proxy_async();   // the zero fill above precedes every bulk copy into the same bytes
+    __syncthreads();
     const Geometry g = make_geometry(a, window);
+    // 160 threads x 168 registers at launch = 4 consumer warps x 200 + the loader warp x 40: each scheduler's register file
+    // holds two consumer warps (one per resident CTA) and the loaders
     if (threadIdx.x >= NW * 32) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS));
-        producer_loop(a, n_groups, g, smem, sched);
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(LOADER_REGS));
+        loader_loop(a, n_groups, g, smem, sched);
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS));
         consumer_loop(a, n_groups, g, smem, sched);
@@ -511,116 +542,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) dtw_pairs_stream4_kernel(DtwPairs
 
 }  // namespace
 
-// Static schedule of the producer warps (see the kernel header). Batch c (0 .. n_super-1) is stored while the consumers
-// run super-step c (steps 2c-1, 2c; c = 0 is their prologue) and is first read in super-step c+1. Invariants, checked
-// here and again by tests/test_host_logic.py through rp_debug_stream4_schedule:
-//  (1) row pair k is stored before the step that reads it first, look-ahead included: batch <= (st_first(k) - 2) / 2;
-//  (2) ring slot k % 16 is free: the last read of row pair k-16 lies DEPTH super-steps before the batch's (the
-//      producers run up to DEPTH super-steps ahead of the consumers);
-//  (3) the four quarters of window block B >= 4 are stored before the super-step of the step after which its warp
-//      switches to it, and DEPTH super-steps after the one in which block B-2 (same staging slot) was read.
-// Across groups nothing overlaps: the producers wait for the consumers' end-of-group signal before batch 0.
-bool build_stream4_schedule(int m, int n, int band, Stream4Sched* out, int* n_super_out) {
-    Stream4Sched s;
-    std::memset(&s, 0, sizeof(s));
-    const int diff = m > n ? m - n : n - m;
-    const int w = band > diff ? band : diff;
-    if (m < 2 || n < 1 || w < MIN_WINDOW || w > MAX_WINDOW) return false;
-    const int n_blocks = (n + CB - 1) / CB;
-    const int half = m / 2;
-    const int steps = half + SIGMA * (n_blocks - 1);
-    const int n_super = (steps + 1) / 2;
-    if (n_super + 1 > STREAM4_MAX_BATCHES) return false;
-    const int fin0 = 4 + (w + 1) / 2;
-    const int kmax = (m + 1) / 2;
-    auto b_min = [&](int k) { return k > fin0 ? (k - fin0 + 3) / 4 : 0; };
-    auto b_max = [&](int k) { const int b = (k - 1 + w / 2) / 4; return b < n_blocks - 1 ? b : n_blocks - 1; };
-    auto st_first = [&](int k) { return k + SIGMA * b_min(k); };
-    auto st_last = [&](int k) { return k + SIGMA * b_max(k); };
-    auto s_sw = [&](int B) { return PITCH * (B - NW) + fin0; };      // step after which block B replaces block B-4
-    auto c_due = [&](int B) { return (s_sw(B) + 1) / 2 - 1; };         // last batch that may store block B
-    int kf = 1, qB = NW, qj = 0;
-    for (int c = 0; c < n_super; c++) {
-        int slot = 0;
-        while (kf <= kmax && st_first(kf) <= 2 * c + 3) {
-            if (slot == 4) return false;
-            if (kf > SLOTS && (st_last(kf - SLOTS) + 1) / 2 > c - DEPTH) return false;   // (2)
-            s.unit[c][slot++] = (unsigned short)kf++;
-        }
-        while (qB < n_blocks && slot < 4 && c >= c_due(qB) - 2) {
-            if (c > c_due(qB)) return false;                                            // (3) too late
-            if (qB - 2 >= NW && (s_sw(qB - 2) + 1) / 2 > c - DEPTH) return false;       // (3) slot still in use
-            s.unit[c][slot++] = (unsigned short)(0x8000u | (unsigned)(qB << 2) | (unsigned)qj);
-            if (++qj == 4) {
-                qj = 0;
-                qB++;
-            }
-        }
-    }
-    // every row pair a step reads and every block a warp switches to inside the loop must have been scheduled
-    for (int k = 1; k <= kmax && k <= half + 1; k++) {
-        const bool read = b_min(k) <= b_max(k) && st_first(k) <= steps + 1;
-        if (read && k >= kf) return false;
-    }
-    for (int B = NW; B < n_blocks; B++)
-        if (s_sw(B) < steps && B >= qB) return false;
-    // consumers: one control word per (warp, step)
-    auto mask = [&](int u, int c0) {
-        const int t = 2 * u - c0 + w - 2;
-        const int lo = std::min(std::max(7 - t, 0), 10), hi = std::min(std::max(7 - t + 2 * w, 0), 10);
-        return (1u << hi) - (1u << lo);
-    };
-    for (int wq = 0; wq < NW; wq++) {
-        int B = wq;
-        for (int st = 1; st <= steps; st++) {
-            const int u = st - SIGMA * B;
-            const int ufirst = std::max(1, 4 * B + 1 - w / 2), ulast = 4 * B + fin0;
-            if (B >= n_blocks || u < ufirst || u > ulast) continue;
-            const int c0 = B * CB + 1;
-            const unsigned M = mask(u, c0);
-            unsigned c = CTL_ACTIVE | (M << CTL_MASK_SHIFT) | ((unsigned)(u & 15) << CTL_SLOT_SHIFT);
-            if (u == ufirst) c |= CTL_FRESH;
-            if ((M & 0x1ffu) == 0x1ffu) c |= CTL_FULL;
-            // v5 (dtw_stream5_kernel.cu): the raw template rows are scaled to unit length by the warp that reads them first,
-            // i.e. by block b_min(k) of row pair k (lower blocks never need it, higher ones run SIGMA steps later each)
-            if (B == b_min(u) && 2 * u <= m) c |= 1u << 26;                                   // CTL_NORM_A: row 2u, loaded in H1
-            if (u + 1 <= ulast && B == b_min(u + 1) && 2 * u + 1 <= m) c |= 1u << 27;         // CTL_NORM_B: row 2u+1, look-ahead load
-            if (u == ufirst && B == b_min(u) && 2 * u - 1 <= m) c |= 1u << 28;                // CTL_NORM_F: row 2u-1, fresh load
-            if (B > 0) {
-                c |= CTL_HAS_LEFT;
-                if ((M >> 8) & 1u) c |= CTL_OK1;
-                if ((M >> 9) & 1u) c |= CTL_OK2;
-                if (u == ufirst && ((mask(u - 1, c0) >> 9) & 1u)) c |= CTL_OK2PREV;
-                if (u == 4 * (B - 1) + fin0 + 1) c |= CTL_DRAIN_RD;
-            }
-            if (u == ulast && st < steps) {
-                c |= CTL_SWITCH;
-                if (B + NW < n_blocks) c |= CTL_NEXT_EXISTS;
-                if ((B + NW) & 1) c |= CTL_NEXT_PARITY;
-                if (B + NW == n_blocks - 1) c |= CTL_NEXT_LAST;
-                s.ctl[wq][st] = c;
-                B += NW;
-                continue;
-            }
-            s.ctl[wq][st] = c;
-        }
-    }
-    {
-        const int Bl = n_blocks - 1, u = steps + 1 - SIGMA * Bl;
-        s.res_from_drain = Bl > 0 && u == 4 * (Bl - 1) + fin0 + 1;
-        s.res_slot = u & (XS - 1);
-    }
-    if (out) *out = s;
-    if (n_super_out) *n_super_out = n_super;
-    return true;
-}
-
-bool dtw_pairs_stream4_supported(const DtwPairsArgs& a) {
-    if (a.d != kD || a.cmn || a.tmpl_len || a.win_len) return false;
+bool dtw_pairs_stream5_supported(const DtwPairsArgs& a) {
+    // dense layout only: bulk copies need 16-byte aligned sources, which per-pair offsets do not promise
+    if (a.d != kD || a.cmn || a.tmpl_len || a.win_len || a.tmpl_off || a.win_off) return false;
+    if ((reinterpret_cast<uintptr_t>(a.tmpl) | reinterpret_cast<uintptr_t>(a.win)) & 15u) return false;
     return build_stream4_schedule(a.tmpl_len_max, a.win_len_max, a.band, nullptr, nullptr);
 }
 
-cudaError_t launch_dtw_pairs_stream4(const DtwPairsArgs& a, cudaStream_t stream) {
+cudaError_t launch_dtw_pairs_stream5(const DtwPairsArgs& a, cudaStream_t stream) {
     if (a.n_pairs <= 0) return cudaSuccess;
     const int m = a.tmpl_len_max, n = a.win_len_max;
     const int diff = m > n ? m - n : n - m;
@@ -628,17 +557,17 @@ cudaError_t launch_dtw_pairs_stream4(const DtwPairsArgs& a, cudaStream_t stream)
     Stream4Sched sched;
     if (!build_stream4_schedule(m, n, a.band, &sched, nullptr)) return cudaErrorInvalidValue;
     const int64_t n_groups = (a.n_pairs + PPG - 1) / PPG;
-    cudaError_t e = cudaFuncSetAttribute(dtw_pairs_stream4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(dtw_pairs_stream5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 148, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dtw_pairs_stream4_kernel, NTHREADS, SMEM_BYTES);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dtw_pairs_stream5_kernel, NTHREADS, SMEM_BYTES);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     int64_t blocks = (int64_t)sms * per_sm;
     if (blocks > n_groups) blocks = n_groups;
-    dtw_pairs_stream4_kernel<<<(unsigned)blocks, NTHREADS, SMEM_BYTES, stream>>>(a, n_groups, window, sched);
+    dtw_pairs_stream5_kernel<<<(unsigned)blocks, NTHREADS, SMEM_BYTES, stream>>>(a, n_groups, window, sched);
     return cudaGetLastError();
 }
 
