@@ -14,11 +14,12 @@
 // the consumers) and the consumers spend 21 % of their time at the full/empty barrier; the consumers' step body alone,
 // fed from shared memory with nothing else running, needs 633 cycles per step at this occupancy against 1383 in the
 // kernel (tools/microbench_k2s_ceiling.cu, profiles/r02_k2s_ceiling.txt). So:
-//  * ONE loader warp per CTA replaces the producers. Lane = pair: per unit of the host-built schedule (a template row
-//    pair or a quarter of a window block: 128 contiguous bytes of one pair) every lane issues one bulk async copy
+//  * Four LOADER warps per CTA replace the producers, one per unit of a batch. Lane = pair: for its unit of the host-built
+//    schedule (a template row pair or a quarter of a window block: 128 contiguous bytes of one pair) every lane issues one bulk async copy
 //    (cp.async.bulk.shared.global, the TMA path: UBLKCP in SASS) straight into the ring / staging slot; completion is
 //    counted in bytes on an mbarrier per batch (SYNCS.ARRIVE.TRANS64). No data passes through registers, ~10 instructions
-//    per unit and warp instead of ~160.
+//    per unit and warp instead of ~160. (Four warps rather than one so that, as in v4, each scheduler's register file hosts
+//    exactly one 200-register consumer warp per resident CTA: setmaxnreg can only grow a warp inside its own scheduler.)
 //  * The RAW rows are normalised by the consumer that touches them first: the host-built control word says when a row
 //    load is the first read of that row by any warp (always block b_min(k) of row pair k); that warp scales the row to
 //    unit length in registers (it needs it there anyway) and writes it back, every later reader — at least one
@@ -43,7 +44,8 @@ namespace {
 constexpr int kD = 16;
 constexpr int CB = 8;                                 // window columns per block
 constexpr int NW = 4;                                 // consumer warps per CTA = blocks of one pair in flight
-constexpr int NTHREADS = NW * 32 + 32;                // + one loader warp
+constexpr int NTHREADS = 2 * NW * 32;                 // + four loader warps (one per unit of a batch): warp w sits on scheduler w % 4,
+                                                      // so every scheduler hosts one consumer and one loader warp per CTA
 constexpr int PPG = 32;                               // pairs per group (one per lane)
 constexpr int SIGMA = 2;                              // block b runs SIGMA steps behind block b-1
 constexpr int PITCH = 4 + SIGMA;                      // steps between the starts of consecutive blocks
@@ -468,6 +470,7 @@ __device__ __forceinline__ void consumer_loop(const DtwPairsArgs& a, int64_t n_g
 // Lane = pair: every unit is 128 contiguous bytes of the lane's pair in global memory and in its ring / staging slot.
 __device__ __forceinline__ void loader_loop(const DtwPairsArgs& a, int64_t n_groups, const Geometry& g, float* smem, const Stream4Sched& sched) {
     const int lane = threadIdx.x & 31;
+    const int unit = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5) - NW, 0);   // warp-uniform: which of the batch's four units
     const int m = g.m, n = g.n;
     const unsigned smem_a = (unsigned)__cvta_generic_to_shared(smem);
     const unsigned ring_a = smem_a + (unsigned)(lane * RING_PAIR_F * 4);
@@ -484,35 +487,25 @@ __device__ __forceinline__ void loader_loop(const DtwPairsArgs& a, int64_t n_gro
             // or by the previous group
             if (c >= DEPTH) bar_sync(BAR_EMPTY + ((c - DEPTH) & 3));
             else if (c == 0 && grp != (int64_t)blockIdx.x) bar_sync(BAR_GROUP);
-            const float* src[4];
-            unsigned dst[4], bytes[4], total = 0;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const unsigned un = sched.unit[c][i];
-                src[i] = nullptr;
-                dst[i] = 0;
-                bytes[i] = 0;
-                if (un & 0x8000u) {   // two window columns (a quarter block); columns >= n are not copied (their cells are never read)
-                    const int Bq = (un & 0x7fffu) >> 2, j = un & 3u;
-                    const int c0 = Bq * CB + 2 * j;
-                    const int valid = min(max(n - c0, 0), 2);
-                    src[i] = winf + (size_t)c0 * kD;
-                    dst[i] = stage_a + (unsigned)(((Bq & 1) * (CB * kD) + 2 * j * kD) * 4);
-                    bytes[i] = (unsigned)valid * (kD * 4);
-                } else if (un) {      // template rows 2k-1, 2k (the second one only if it exists)
-                    const int k = (int)un;
-                    src[i] = tmplf + (size_t)(2 * k - 2) * kD;
-                    dst[i] = ring_a + (unsigned)((k & (SLOTS - 1)) * SLOT_F * 4);
-                    bytes[i] = (unsigned)min(max(m - (2 * k - 2), 0), 2) * (kD * 4);
-                }
-                total += bytes[i];
+            const unsigned un = sched.unit[c][unit];
+            const float* src = nullptr;
+            unsigned dst = 0, bytes = 0;
+            if (un & 0x8000u) {   // two window columns (a quarter block); columns >= n are not copied (their cells are never read)
+                const int Bq = (un & 0x7fffu) >> 2, j = un & 3u;
+                const int c0 = Bq * CB + 2 * j;
+                src = winf + (size_t)c0 * kD;
+                dst = stage_a + (unsigned)(((Bq & 1) * (CB * kD) + 2 * j * kD) * 4);
+                bytes = (unsigned)min(max(n - c0, 0), 2) * (kD * 4);
+            } else if (un) {      // template rows 2k-1, 2k (the second one only if it exists)
+                const int k = (int)un;
+                src = tmplf + (size_t)(2 * k - 2) * kD;
+                dst = ring_a + (unsigned)((k & (SLOTS - 1)) * SLOT_F * 4);
+                bytes = (unsigned)min(max(m - (2 * k - 2), 0), 2) * (kD * 4);
             }
             const unsigned bar = full_bar + 8u * (batch & 3u);
-            if (lane == 0) mbar_expect_tx(bar, total * 32u);   // (an empty batch is a plain arrival: its phase still completes)
+            if (lane == 0) mbar_expect_tx(bar, bytes * 32u);   // one arrival per loader warp (an empty unit is a plain arrival)
             __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                if (bytes[i]) bulk_g2s(dst[i], src[i], bytes[i], bar);
+            if (bytes) bulk_g2s(dst, src, bytes, bar);
         }
     }
 }
@@ -523,14 +516,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) dtw_pairs_stream5_kernel(DtwPairs
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned full_bar = (unsigned)__cvta_generic_to_shared(smem + RING_F + STAGE_F + XCH_F + XDRAIN_F);
-        for (unsigned i = 0; i < 4; i++) mbar_init(full_bar + 8u * i, 1u);
+        for (unsigned i = 0; i < 4; i++) mbar_init(full_bar + 8u * i, (unsigned)NW);   // one arrival per loader warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fence_proxy_async();   // the zero fill above precedes every bulk copy into the same bytes
     __syncthreads();
     const Geometry g = make_geometry(a, window);
-    // 160 threads x 168 registers at launch = 4 consumer warps x 200 + the loader warp x 40: each scheduler's register file
-    // holds two consumer warps (one per resident CTA) and the loaders
+    // 256 threads x 128 registers at launch; the loaders hand most of theirs to the consumers. Warp w lives on scheduler w % 4,
+    // so each scheduler's register file holds one consumer and one loader warp of each resident CTA: 2 x (200 + 40) x 32 <= 16 K
     if (threadIdx.x >= NW * 32) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(LOADER_REGS));
         loader_loop(a, n_groups, g, smem, sched);
