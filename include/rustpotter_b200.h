@@ -231,9 +231,8 @@ int rp_dtw_scores(const float* tmpl_dev, const int64_t* tmpl_off_dev, const int3
 /* Selects the DTW kernel variants (0 = automatic, 1 = generic reference-order kernels, 2 = tuned kernels,
  * 3 = tuned with the one-row-per-step streaming kernel, 4 = (retired) same as 2, 5 = tuned with the round-1 two-rows-per-step streaming kernel, 6 = tuned with the v3 streaming kernel
  * (lanes of a warp as the systolic array), 7 = tuned with the pipeline kernel reading its templates from shared
- * instead of constant memory, 8 = tuned with the v4 streaming kernel (producer warps); 0 and 2 take the v5 kernel (warps of a
- * CTA as the systolic array, bulk-copy loader warp, first-touch normalisation) for dense pairs with windows 3..20, v4 for
- * pairs with offsets). For A/B measurements and parity tests. */
+ * instead of constant memory; 0 and 2 take the v4 kernel (warps of a CTA as the systolic array,
+ * producer/consumer warpgroups) for windows 3..20). For A/B measurements and parity tests. */
 int rp_set_dtw_variant(int variant);
 /* Avg gate of the batched window scorer: 1 / -1 (default) = score avg_features first and the templates only where the
  * gate can pass, as the reference does; 0 = every template of every window (dense score tensor; parity taps, A/B). The

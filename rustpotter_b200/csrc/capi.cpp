@@ -711,10 +711,9 @@ int rp_set_dtw_variant(int v) {
     // 0 automatic, 1 generic kernels, 2 tuned kernels, 3 tuned with the one-row-per-step streaming kernel,
     // 4 tuned with the two-windows-per-thread pipeline kernel, 5 tuned with the round-1 two-rows-per-step
     // streaming kernel, 6 tuned with the v3 streaming kernel, 7 tuned with the pipeline kernel reading its templates from
-    // shared instead of constant memory, 8 tuned with the v4 streaming kernel (producer warps) where v5 would apply
-    // (alternatives kept for A/B measurements)
+    // shared instead of constant memory (alternatives kept for A/B measurements)
     g_dtw_variant.store(v >= 3 ? 2 : v);
-    set_dtw_stream_rows(v == 3 ? 1 : (v == 5 ? 2 : (v == 6 ? 3 : (v == 8 ? 4 : 0))));
+    set_dtw_stream_rows(v == 3 ? 1 : (v == 5 ? 2 : (v == 6 ? 3 : 0)));
     set_dtw_window_kernel(v == 7 ? 3 : 0);
     return RP_OK;
 }

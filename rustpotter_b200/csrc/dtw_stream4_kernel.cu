@@ -581,11 +581,6 @@ bool build_stream4_schedule(int m, int n, int band, Stream4Sched* out, int* n_su
             unsigned c = CTL_ACTIVE | (M << CTL_MASK_SHIFT) | ((unsigned)(u & 15) << CTL_SLOT_SHIFT);
             if (u == ufirst) c |= CTL_FRESH;
             if ((M & 0x1ffu) == 0x1ffu) c |= CTL_FULL;
-            // v5 (dtw_stream5_kernel.cu): the raw template rows are scaled to unit length by the warp that reads them first,
-            // i.e. by block b_min(k) of row pair k (lower blocks never need it, higher ones run SIGMA steps later each)
-            if (B == b_min(u) && 2 * u <= m) c |= 1u << 26;                                   // CTL_NORM_A: row 2u, loaded in H1
-            if (u + 1 <= ulast && B == b_min(u + 1) && 2 * u + 1 <= m) c |= 1u << 27;         // CTL_NORM_B: row 2u+1, look-ahead load
-            if (u == ufirst && B == b_min(u) && 2 * u - 1 <= m) c |= 1u << 28;                // CTL_NORM_F: row 2u-1, fresh load
             if (B > 0) {
                 c |= CTL_HAS_LEFT;
                 if ((M >> 8) & 1u) c |= CTL_OK1;

@@ -475,8 +475,6 @@ bool dtw_pairs_stream3_supported(const DtwPairsArgs& a);
 cudaError_t launch_dtw_pairs_stream3(const DtwPairsArgs& a, cudaStream_t stream);
 bool dtw_pairs_stream4_supported(const DtwPairsArgs& a);
 cudaError_t launch_dtw_pairs_stream4(const DtwPairsArgs& a, cudaStream_t stream);
-bool dtw_pairs_stream5_supported(const DtwPairsArgs& a);
-cudaError_t launch_dtw_pairs_stream5(const DtwPairsArgs& a, cudaStream_t stream);
 
 bool dtw_pairs_stream_supported(const DtwPairsArgs& a) {
     if (a.d != kD || a.cmn || a.tmpl_len || a.win_len) return false;
@@ -493,9 +491,7 @@ bool dtw_pairs_stream_supported(const DtwPairsArgs& a) {
 cudaError_t launch_dtw_pairs_stream(const DtwPairsArgs& a, cudaStream_t stream) {
     if (a.n_pairs <= 0) return cudaSuccess;
     // 0: newest kernel that supports the shape; 3: v3 (lanes of a warp as the systolic array); 1, 2: round-1 kernels
-    // 4: v4 (producer warps) even where v5 (bulk-copy loader, first-touch normalisation) applies
-    if (g_stream_rows == 0 && dtw_pairs_stream5_supported(a)) return launch_dtw_pairs_stream5(a, stream);
-    if ((g_stream_rows == 0 || g_stream_rows == 4) && dtw_pairs_stream4_supported(a)) return launch_dtw_pairs_stream4(a, stream);
+    if (g_stream_rows == 0 && dtw_pairs_stream4_supported(a)) return launch_dtw_pairs_stream4(a, stream);
     if ((g_stream_rows == 0 || g_stream_rows == 3) && dtw_pairs_stream3_supported(a)) return launch_dtw_pairs_stream3(a, stream);
     const int m = a.tmpl_len_max, n = a.win_len_max;
     const int diff = m > n ? m - n : n - m;
