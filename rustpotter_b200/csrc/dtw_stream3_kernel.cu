@@ -2,7 +2,7 @@
 //
 // Contract: reference src/mfcc/comparator.rs:18-26 over src/mfcc/dtw.rs:56-105 (banded DTW with the
 // asymmetric band [r-w, r+w-1], result cell D[m-1][n], cosine distance with similarity 0 for zero
-// vectors, cost/(m+n) -> logistic score). Same mapping family as dtw_stream_kernel.cu ("column-block
+// vectors, cost/(m+n) -> logistic score). Same mapping family as the retired round-1 kernel ("column-block
 // systolic array": 5 lanes per pair, 6 pairs per warp, a lane keeps one block of 8 window columns as
 // negated unit vectors in registers and walks the template two rows per step; template rows stream
 // through a cp.async ring in shared memory), rebuilt around what the round-1 ncu source page showed:
