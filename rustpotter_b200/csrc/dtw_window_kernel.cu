@@ -126,6 +126,7 @@ struct WindowLaunch {              // what one launch covers (device pointers)
     int n_wakewords;
     unsigned char* tile_pass;      // [n_streams][j_blocks][n_wakewords]
     int band;                      // band_size (MASK instances)
+    long long const_base;          // CT: float offset in tmpl_unit of the range that c_tmpl_unit currently holds
 };
 
 template <int W, bool CT, bool MASK>
@@ -154,7 +155,7 @@ dtw_windows_d16_kernel(DtwWindowsArgs a, WindowLaunch L, const float* __restrict
     if (L.gate == 2 && L.tile_pass[(b * j_blocks + jb) * L.n_wakewords + L.slot_ww[s]] == 0) return;
     const int j0 = a.first_window + jb * kNW;
     const int m = a.slot_len[s];
-    const int c_row0 = CT ? (int)(L.unit_off[s] >> 2) : 0;   // float4 index of the slot's first row in c_tmpl_unit
+    const int c_row0 = CT ? (int)((L.unit_off[s] - L.const_base) >> 2) : 0;   // float4 index of the slot's first row in c_tmpl_unit
     // MASK: band offsets i (column c = r - W + i) inside the reference's band [r-band, r+band-1]
     const unsigned long long band_mask = MASK ? (((1ull << (2 * L.band)) - 1ull) << (W - L.band)) : ~0ull;
 
@@ -361,6 +362,7 @@ namespace {
 struct ConstOwner {
     const float* src = nullptr;
     uint64_t version = 0;
+    size_t begin = 0, floats = 0;   // the range of src that the constant copy holds (a whole set, or one wakeword's templates)
     const float* challenger = nullptr;
     uint64_t challenger_version = 0;
     int challenger_launches = 0;
@@ -370,10 +372,19 @@ ConstOwner g_const_owner[64];
 std::mutex g_const_mu;
 
 // Called with g_const_mu held; true: the constant copy is this template set's and stays so until the lock is released.
-bool const_templates_mine(int dev, const float* tmpl_unit, size_t tmpl_floats, uint64_t version, cudaStream_t stream, cudaError_t* err) {
+// [begin, begin + floats) of tmpl_unit is what this launch reads. The owner may move its range from launch to launch (one
+// wakeword's templates at a time when the whole set exceeds 64 KB): its launches run on one stream, so the copy is ordered
+// between the kernels that read the old and the new range.
+bool const_templates_mine(int dev, const float* tmpl_unit, size_t begin, size_t floats, uint64_t version, cudaStream_t stream, cudaError_t* err) {
     ConstOwner& o = g_const_owner[dev];
     if (o.src == tmpl_unit && o.version == version) {
         o.challenger = nullptr;
+        if (o.begin != begin || o.floats != floats) {
+            *err = cudaMemcpyToSymbolAsync(c_tmpl_unit, tmpl_unit + begin, floats * sizeof(float), 0, cudaMemcpyDeviceToDevice, stream);
+            if (*err != cudaSuccess) return false;
+            o.begin = begin;
+            o.floats = floats;
+        }
         return true;
     }
     if (o.src != nullptr) {
@@ -389,17 +400,19 @@ bool const_templates_mine(int dev, const float* tmpl_unit, size_t tmpl_floats, u
         *err = cudaDeviceSynchronize();
         if (*err != cudaSuccess) return false;
     }
-    *err = cudaMemcpyToSymbolAsync(c_tmpl_unit, tmpl_unit, tmpl_floats * sizeof(float), 0, cudaMemcpyDeviceToDevice, stream);
+    *err = cudaMemcpyToSymbolAsync(c_tmpl_unit, tmpl_unit + begin, floats * sizeof(float), 0, cudaMemcpyDeviceToDevice, stream);
     if (*err != cudaSuccess) return false;
     o.src = tmpl_unit;
     o.version = version;
+    o.begin = begin;
+    o.floats = floats;
     o.challenger = nullptr;
     return true;
 }
 
 template <int W, bool MASK>
-cudaError_t launch_instance(const DtwWindowsArgs& a, const WindowLaunch& L, const float* tmpl_unit, size_t tmpl_floats, uint64_t tmpl_version,
-                            int j_blocks, cudaStream_t stream) {
+cudaError_t launch_instance(const DtwWindowsArgs& a, WindowLaunch L, const float* tmpl_unit, size_t const_begin, size_t const_floats,
+                            uint64_t tmpl_version, int j_blocks, cudaStream_t stream) {
     const int64_t ctas = a.n_streams * (int64_t)j_blocks * L.n_slots;
     if (ctas <= 0) return cudaSuccess;
     if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
@@ -412,9 +425,10 @@ cudaError_t launch_instance(const DtwWindowsArgs& a, const WindowLaunch& L, cons
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lock(g_const_mu);   // (the launch below happens while the ownership is known)
     cudaError_t e0 = cudaSuccess;
-    const bool ct = g_window_kernel.load() != 3 && tmpl_floats > 0 && tmpl_floats <= (size_t)kConstRows * kD && dev >= 0 && dev < 64 &&
-                    const_templates_mine(dev, tmpl_unit, tmpl_floats, tmpl_version, stream, &e0);
+    const bool ct = g_window_kernel.load() != 3 && const_floats > 0 && const_floats <= (size_t)kConstRows * kD && dev >= 0 && dev < 64 &&
+                    const_templates_mine(dev, tmpl_unit, const_begin, const_floats, tmpl_version, stream, &e0);
     if (e0 != cudaSuccess) return e0;
+    L.const_base = (long long)const_begin;
     if (ct) {
         cudaError_t e = cudaFuncSetAttribute(dtw_windows_d16_kernel<W, true, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
@@ -449,11 +463,15 @@ cudaError_t launch_dtw_windows_d16(const DtwWindowsArgs& a, const WindowGate& g,
     L.n_wakewords = g.n_wakewords;
     L.tile_pass = g.tile_pass;
     L.band = a.band;
-    if (a.band == 5) return launch_instance<5, false>(a, L, tmpl_unit, tmpl_floats, tmpl_version, j_blocks, stream);
-    if (a.band < 5) return launch_instance<5, true>(a, L, tmpl_unit, tmpl_floats, tmpl_version, j_blocks, stream);
-    if (a.band <= 8) return launch_instance<8, true>(a, L, tmpl_unit, tmpl_floats, tmpl_version, j_blocks, stream);
-    if (a.band <= 12) return launch_instance<12, true>(a, L, tmpl_unit, tmpl_floats, tmpl_version, j_blocks, stream);
-    return launch_instance<20, true>(a, L, tmpl_unit, tmpl_floats, tmpl_version, j_blocks, stream);
+    L.const_base = 0;
+    // what the constant-memory copy of the templates should hold for this launch: the whole set, one range of it, or nothing
+    const size_t cb = g.const_floats > 0 ? (size_t)g.const_begin : 0;
+    const size_t cf = g.const_floats > 0 ? (size_t)g.const_floats : (g.const_floats < 0 ? 0 : tmpl_floats);
+    if (a.band == 5) return launch_instance<5, false>(a, L, tmpl_unit, cb, cf, tmpl_version, j_blocks, stream);
+    if (a.band < 5) return launch_instance<5, true>(a, L, tmpl_unit, cb, cf, tmpl_version, j_blocks, stream);
+    if (a.band <= 8) return launch_instance<8, true>(a, L, tmpl_unit, cb, cf, tmpl_version, j_blocks, stream);
+    if (a.band <= 12) return launch_instance<12, true>(a, L, tmpl_unit, cb, cf, tmpl_version, j_blocks, stream);
+    return launch_instance<20, true>(a, L, tmpl_unit, cb, cf, tmpl_version, j_blocks, stream);
 }
 
 }  // namespace rp

@@ -156,6 +156,27 @@ void Engine::configure(const WakewordSet& ws, const rp_config& cfg) {
         }
         n_avg_slots_ = (int)avg_slots.size();
         n_tmpl_slots_ = (int)tmpl_slots.size();
+        std::vector<int32_t> all_slots((size_t)n_slots_);
+        for (int s2 = 0; s2 < n_slots_; s2++) all_slots[(size_t)s2] = s2;
+        upload(all_slots_, all_slots, stream_, "slot ids");
+        ww_ranges_.clear();
+        bool each_fits = true;
+        int tl = 0;
+        for (size_t w = 0; w < ws.metas.size(); w++) {
+            const WakewordMeta& mt = ws.metas[w];
+            WakewordRange r;
+            r.slot_begin = mt.slot_begin;
+            r.n_slots = mt.n_templates + (mt.has_avg ? 1 : 0);
+            r.tmpl_list_begin = tl;
+            r.n_templates = mt.n_templates;
+            tl += mt.n_templates;
+            r.unit_begin = uoff[(size_t)r.slot_begin];
+            const int last = r.slot_begin + r.n_slots - 1;
+            r.unit_floats = uoff[(size_t)last] + (int64_t)len[(size_t)last] * dp - r.unit_begin;
+            each_fits = each_fits && r.unit_floats <= kWindowConstFloats;
+            ww_ranges_.push_back(r);
+        }
+        per_wakeword_const_ = (int64_t)unit.size() > kWindowConstFloats && each_fits && ws.metas.size() > 1;
         upload(avg_slots_, avg_slots, stream_, "avg slots");
         upload(tmpl_slots_, tmpl_slots, stream_, "template slots");
         upload(slot_ww_, slot_ww, stream_, "slot wakewords");
@@ -397,6 +418,9 @@ void Engine::process(const AudioIn& in, bool want_vad, int first_window, std::ve
             wg.slot_ww = slot_ww_.as<int32_t>();
             wg.metas = metas_.as<WakewordMeta>();
             wg.n_wakewords = n_wakewords_;
+            auto launch = [&](const char* what) {
+                cuda_check(launch_dtw_windows_d16(wa, wg, tmpl_unit_.as<float>(), tmpl_unit_floats_, tmpl_version_, stream_), what);
+            };
             if (gated) {
                 // wakeword_comp.rs:85-94: avg_features first; templates only where some window of the tile passes the avg gate
                 wg.tile_pass = tile_pass_.as<unsigned char>() + (size_t)b0 * j_blocks * n_wakewords_;
@@ -404,14 +428,36 @@ void Engine::process(const AudioIn& in, bool want_vad, int first_window, std::ve
                 wg.slots = avg_slots_.as<int32_t>();
                 wg.n_slots = n_avg_slots_;
                 wg.gate = 1;
-                cuda_check(launch_dtw_windows_d16(wa, wg, tmpl_unit_.as<float>(), tmpl_unit_floats_, tmpl_version_, stream_), "dtw window kernel (avg)");
-                wg.slots = tmpl_slots_.as<int32_t>();
-                wg.n_slots = n_tmpl_slots_;
+                wg.const_floats = per_wakeword_const_ ? -1 : 0;   // (the avg slots of several wakewords: shared-memory templates)
+                launch("dtw window kernel (avg)");
                 wg.gate = 2;
-                cuda_check(launch_dtw_windows_d16(wa, wg, tmpl_unit_.as<float>(), tmpl_unit_floats_, tmpl_version_, stream_), "dtw window kernel (templates)");
-                launches += 1;
+                if (per_wakeword_const_) {
+                    for (const WakewordRange& r : ww_ranges_) {   // one wakeword's templates in constant memory at a time
+                        wg.slots = tmpl_slots_.as<int32_t>() + r.tmpl_list_begin;
+                        wg.n_slots = r.n_templates;
+                        wg.const_begin = r.unit_begin;
+                        wg.const_floats = r.unit_floats;
+                        launch("dtw window kernel (templates)");
+                        launches += 1;
+                    }
+                } else {
+                    wg.slots = tmpl_slots_.as<int32_t>();
+                    wg.n_slots = n_tmpl_slots_;
+                    launch("dtw window kernel (templates)");
+                    launches += 1;
+                }
+            } else if (per_wakeword_const_) {
+                for (const WakewordRange& r : ww_ranges_) {
+                    wg.slots = all_slots_.as<int32_t>() + r.slot_begin;
+                    wg.n_slots = r.n_slots;
+                    wg.const_begin = r.unit_begin;
+                    wg.const_floats = r.unit_floats;
+                    launch("dtw window kernel");
+                    launches += 1;
+                }
+                launches -= 1;
             } else {
-                cuda_check(launch_dtw_windows_d16(wa, wg, tmpl_unit_.as<float>(), tmpl_unit_floats_, tmpl_version_, stream_), "dtw window kernel");
+                launch("dtw window kernel");
             }
         } else {
             cuda_check(launch_dtw_windows_generic(wa, stream_), "dtw kernel");

@@ -128,7 +128,14 @@ class Engine {
     float score_ref_ = 0.22f;
     DeviceBuffer tmpl_, tmpl_unit_, slot_off_, slot_len_, metas_;
     DeviceBuffer unit_off_, avg_slots_, tmpl_slots_, slot_ww_;   // tuned window kernel: padded-template offsets, launch lists
+    DeviceBuffer all_slots_;   // identity list 0 .. n_slots-1 (sub-lists = one wakeword's slots)
     int n_avg_slots_ = 0, n_tmpl_slots_ = 0;
+    struct WakewordRange {     // where one wakeword sits in the slot lists and in tmpl_unit_
+        int slot_begin, n_slots, tmpl_list_begin, n_templates;
+        int64_t unit_begin, unit_floats;
+    };
+    std::vector<WakewordRange> ww_ranges_;
+    bool per_wakeword_const_ = false;   // the set exceeds the kernel's constant-memory copy but every wakeword fits: one launch each
     DeviceBuffer tile_pass_;   // [B][j_blocks][n_wakewords] avg-gate verdict per window tile
     int last_j_blocks_ = 0, last_first_window_ = 0;
     bool last_gated_ = false;

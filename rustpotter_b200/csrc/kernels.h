@@ -102,7 +102,12 @@ struct WindowGate {
     const WakewordMeta* metas = nullptr;
     int n_wakewords = 0;
     unsigned char* tile_pass = nullptr;  // [n_streams][ceil((n_new - first_window) / dtw_windows_tile())][n_wakewords]
+    // constant-memory copy of the unit templates (64 KB): const_floats == 0: the whole set if it fits; > 0: the range
+    // [const_begin, const_begin + const_floats) of tmpl_unit, which must hold every slot of this launch (one wakeword's
+    // templates when the set as a whole does not fit); < 0: do not use it for this launch
+    int64_t const_begin = 0, const_floats = 0;
 };
+constexpr int64_t kWindowConstFloats = 1024 * 16;   // capacity of that copy
 bool dtw_windows_tuned_supported(int d, int band, int max_slot_len, int window_len);
 int dtw_windows_tile();                  // windows per CTA tile (the granularity of the avg gate)
 cudaError_t launch_dtw_windows_d16(const DtwWindowsArgs& a, const WindowGate& g, const float* tmpl_unit, size_t tmpl_floats,
