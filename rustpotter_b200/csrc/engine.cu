@@ -341,7 +341,10 @@ void Engine::process(const AudioIn& in, bool want_vad, int first_window, std::ve
     const int fw = std::min(std::max(first_window, 0), n_new);
     const int tile = dtw_windows_tile();
     const int j_blocks = (n_new - fw + tile - 1) / tile;
-    const bool gated = tuned && avg_gate_ && n_avg_slots_ > 0 && n_tmpl_slots_ > 0 && j_blocks > 0;
+    // short calls (the reference's 30 ms cadence: three windows per stream) take the warp-per-window-triple kernel
+    const bool cadence = tuned && dtw_variant_ != 9 && n_new - fw > 0 && n_new - fw <= dtw_windows_cadence_max_new() &&
+                         dtw_windows_cadence_supported(d_, band_, max_slot_len_, max_frames_);
+    const bool gated = tuned && !cadence && avg_gate_ && n_avg_slots_ > 0 && n_tmpl_slots_ > 0 && j_blocks > 0;
     if (gated) tile_pass_.reserve((size_t)n_streams_ * j_blocks * n_wakewords_, "avg-gate tiles");
     last_gated_ = gated;
     last_j_blocks_ = j_blocks;
@@ -412,7 +415,9 @@ void Engine::process(const AudioIn& in, bool want_vad, int first_window, std::ve
             cuda_check(cudaMemset2DAsync(wa.scores, (size_t)n_new * n_slots_ * sizeof(float), 0xff,
                                          (size_t)wa.first_window * n_slots_ * sizeof(float), (size_t)nb, stream_), "memset skipped rows");
         // (an avg_features matrix longer than every template scores a window shorter than itself: generic kernel only)
-        if (tuned) {
+        if (cadence) {
+            cuda_check(launch_dtw_windows_cadence(wa, tmpl_unit_.as<float>(), unit_off_.as<int64_t>(), stream_), "dtw cadence kernel");
+        } else if (tuned) {
             WindowGate wg;
             wg.unit_off = unit_off_.as<int64_t>();
             wg.slot_ww = slot_ww_.as<int32_t>();

@@ -113,6 +113,10 @@ int dtw_windows_tile();                  // windows per CTA tile (the granularit
 cudaError_t launch_dtw_windows_d16(const DtwWindowsArgs& a, const WindowGate& g, const float* tmpl_unit, size_t tmpl_floats,
                                    uint64_t tmpl_version, cudaStream_t stream);
 void set_dtw_window_kernel(int v);  // 0 = templates from constant memory when they fit, 3 = always shared memory (debug)
+// Short calls (dtw_cadence_kernel.cu): one warp per (stream, template, three consecutive windows). d <= 16, band <= 5.
+int dtw_windows_cadence_max_new();      // the engine takes this kernel when a call brings at most this many windows per stream
+bool dtw_windows_cadence_supported(int d, int band, int max_slot_len, int window_len);
+cudaError_t launch_dtw_windows_cadence(const DtwWindowsArgs& a, const float* tmpl_unit, const int64_t* unit_off, cudaStream_t stream);
 
 // K3: judge every window, append detections to a compact hit list.
 // hit record (floats/ints, stride = 5 + max_templates): [stream, frame, wakeword, avg_score, score, scores...]

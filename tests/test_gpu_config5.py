@@ -326,3 +326,44 @@ def test_batch_48khz_streams_match_the_per_stream_handle():
     with pytest.raises(rp.RustpotterError):
         import torch
         bt.process(torch.zeros((3, 1440), device="cuda"))
+
+
+# ------------------------------------------------------------------ short calls: the cadence kernel (30 ms chunks)
+@pytest.mark.parametrize("d,band,chunks_per_call", [(16, 5, 1), (16, 5, 2), (16, 5, 8), (5, 5, 1), (16, 3, 1), (13, 1, 3), (16, 5, 9)])
+def test_cadence_kernel_dense_scores_vs_generic_and_pipeline(d, band, chunks_per_call):
+    """Calls of a few 30 ms chunks take the warp-per-window-triple kernel (variant 0); its dense per-window scores equal the
+    reference-order generic kernel's (variant 1) and the pipeline kernel's (variant 9) on the same calls, call by call."""
+    lengths = (50, 44, 57, 50)
+    rpw, utts = make_wakeword(O, d=d, lengths=lengths, seed=500 + d + band)
+    n_calls = 70 // chunks_per_call
+    S = chunks_per_call * 480
+    audio = synth_audio(5, n_calls * S, seed=31)
+    splice(audio[1], utts[2], 70)
+    splice(audio[4], utts[0], 100)
+    res = {}
+    rp.set_avg_gate(0)
+    try:
+        for variant in (1, 9, 0):
+            rp.set_dtw_variant(variant)
+            bt = rp.RustpotterBatch(5, rp.default_config(band_size=band))
+            bt.add_wakeword_from_buffer("w", rpw)
+            out, dets = [], []
+            for c in range(n_calls):
+                dets += [(s, c * chunks_per_call + ch, dd["counter"], float(dd["score"])) for s, ch, dd in bt.process(audio[:, c * S:(c + 1) * S])]
+                out.append(bt.last_scores(chunks_per_call * 3, len(lengths) + 1).copy())
+            res[variant] = (np.concatenate(out, axis=1), dets, bt.windows_scored())
+    finally:
+        rp.set_dtw_variant(0)
+        rp.set_avg_gate(-1)
+    first = max(lengths) + 2
+    ref, got9, got0 = (res[v][0][:, first:] for v in (1, 9, 0))
+    assert np.isfinite(ref).all() and np.isfinite(got0).all()
+    for got in (got9, got0):
+        rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-12)
+        assert rel.max() < 3e-5, (d, band, chunks_per_call, rel.max())
+    # same detections (stream, chunk, counter) from all three, scores within the parity bar
+    assert res[0][2] == res[1][2] == res[9][2]
+    assert [x[:3] for x in res[0][1]] == [x[:3] for x in res[1][1]] == [x[:3] for x in res[9][1]]
+    assert len(res[0][1]) >= 2
+    for x, y in zip(res[0][1], res[1][1]):
+        assert _rel(x[3], y[3]) < SCORE_RTOL
