@@ -320,6 +320,27 @@ def cadence_bench(torch, rp, rpws, score_mode: str, device_index: int):
                         "audio_ms_per_call": S / 16.0, "real_time_factor": round(S / 16.0 / float(np.median(lat)), 2),
                         "stage_ms_per_call": {k: round(v, 3) for k, v in stage.items()}}
     del bt
+    # the per-stream drop-in (`Rustpotter::process_samples`, one 30 ms chunk per call, host f32 in, detection out)
+    det = rp.Rustpotter(rp.default_config(score_mode=score_mode, sample_format="f32"), device=device_index)
+    for i, r in enumerate(rpws):
+        det.add_wakeword_from_buffer(f"w{i}", r)
+    g = torch.Generator(device="cpu").manual_seed(11)
+    x = (0.2 * torch.randn(480 * 400, generator=g)).numpy()
+    for c in range(150):
+        det.process_samples(x[c * 480:(c + 1) * 480])
+    lat = []
+    w0 = det.windows_scored()
+    t0 = time.perf_counter()
+    for c in range(150, 400):
+        t1 = time.perf_counter()
+        det.process_samples(x[c * 480:(c + 1) * 480])
+        lat.append((time.perf_counter() - t1) * 1e3)
+    dt = time.perf_counter() - t0
+    out["single_stream_handle"] = {"calls": len(lat), "ms_per_call_median": round(float(np.median(lat)), 4),
+                                   "ms_per_call_p95": round(float(np.percentile(lat, 95)), 4), "audio_ms_per_call": 30.0,
+                                   "real_time_factor": round(30.0 / float(np.median(lat)), 1),
+                                   "windows_per_s": round((det.windows_scored() - w0) / dt, 1)}
+    del det
     return out
 
 

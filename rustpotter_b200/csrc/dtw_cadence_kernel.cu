@@ -6,14 +6,16 @@
 // G_r[u] = a^_r . x_u shared by the windows that overlap in frame u — but a different mapping. K2p gives every window a
 // thread and needs 128 consecutive windows of one stream to fill a CTA; a 30 ms call has three, so its 36 864 CTAs (4096
 // streams x 9 templates) ran with three live threads each: 7.2 ms per call, whatever the call length (profiles/r02_*).
-// Here ONE WARP scores up to three consecutive windows of one stream against one template:
-//   lanes 0 .. 2W+1   one frame each of the row's shared range: G_r[u] (a 16-dim dot, 8 FFMA2)
-//   lanes 12 .. 14     A_r of window 0 .. 2  (the same dot against the window's mean)
-//   lanes 16 .. 18     the thread-serial in-place band DP of window 0 .. 2 (K2p's, G and A arrive by shuffle)
-// A CTA = all templates ("slots") of one stream's window triple, one warp each (the stream's ~105 frames are staged in
-// shared memory once); the template row, identical for the warp, is read from L2 one row ahead. ~80 warp instructions
-// per template row for three windows: about a sixth of K2p's efficiency on long calls, 14x faster than K2p on short ones.
-// The engine takes this kernel when a call brings at most 24 new windows per stream.
+// Here a HALF-WARP scores up to three consecutive windows of one stream against one template, the two halves of a warp
+// two streams against the same template (so the template row is fetched once for both):
+//   lanes 0 .. 2W+1 of the half   one frame each of the row's shared range: G_r[u] (a 16-dim dot, 8 FFMA2)
+//   lanes 12 .. 14                A_r of window 0 .. 2  (the same dot against the window's mean)
+//   lanes 0 .. 2 again            the thread-serial in-place band DP of window 0 .. 2 (K2p's; G and A arrive by shuffle)
+// A CTA = all templates ("slots") of a stream pair's window triple, one warp each (each stream's ~105 frames are staged
+// in shared memory once); the template row, identical for the warp, is read from L2 one row ahead. ~80 warp instructions
+// per template row for six windows: well below K2p's efficiency on long calls, several times faster on short ones
+// (4096 streams x 36 templates, 30 ms calls: see DESIGN.md section 6). The engine takes this kernel when a call brings at
+// most 24 new windows per stream.
 #include <cfloat>
 #include <cmath>
 
@@ -76,71 +78,74 @@ __device__ __forceinline__ float dot16(const Row16& a, const Row16& b) {
     return hsum(acc);
 }
 
-// grid: n_streams * triples CTAs; block: n_warps * 32 threads; dynamic shared memory:
-//   Xs[x_rows][kXS] frames | per warp: Mu[NWIN][16] (negated means) | per warp: Inv[NWIN][inv_cols]
+// grid: ceil(n_streams / 2) * triples CTAs; block: n_warps * 32 threads; dynamic shared memory:
+//   Xs[2][x_rows][kXS] frames of the two streams | per warp and half: Mu[NWIN][16] (negated means) | Inv[NWIN][inv_cols]
 __global__ void __launch_bounds__(kMaxWarps * 32) dtw_windows_cadence_kernel(DtwWindowsArgs a, const float* __restrict__ tmpl_unit,
                                                                             const int64_t* __restrict__ unit_off, int triples, int x_rows,
                                                                             int inv_cols) {
     extern __shared__ __align__(16) float sm[];
-    float* Xs = sm;
     const int n_warps = blockDim.x >> 5;
-    float* MuAll = Xs + (size_t)x_rows * kXS;
-    float* InvAll = MuAll + (size_t)n_warps * NWIN * kD;
+    float* XsAll = sm;
+    float* MuAll = XsAll + (size_t)2 * x_rows * kXS;
+    float* InvAll = MuAll + (size_t)n_warps * 2 * NWIN * kD;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t b = blockIdx.x / triples;
-    const int q = (int)(blockIdx.x - b * triples);
+    const int half = lane >> 4, hl = lane & 15, hbase = lane & 16;   // half-warp, lane inside it, its first lane
+    const int64_t pair = blockIdx.x / triples;
+    const int q = (int)(blockIdx.x - pair * triples);
     const int j0 = a.first_window + q * NWIN;                 // first window (new frame index) of this triple
     const int n_win = min(NWIN, a.n_new - j0);
 
-    {   // ---- stage the frames of the triple: window jj of this CTA covers tile rows jj .. jj + m - 1
+    // ---- stage the frames of the triple for both streams: window jj covers tile rows jj .. jj + m - 1
+    for (int h = 0; h < 2; h++) {
+        const int64_t b = 2 * pair + h;
+        float* Xh = XsAll + (size_t)h * x_rows * kXS;
         const int64_t row0 = (int64_t)a.first_window_row + j0;
-        const int64_t avail = a.frame_rows - row0;
+        const int64_t avail = b < a.n_streams ? a.frame_rows - row0 : 0;   // (an odd stream count: the last pair's second half is zeros)
         if (a.d == kD) {
             const float* src = a.frames + (b * a.frame_rows + row0) * kD;
             for (int i = tid; i < x_rows * 4; i += blockDim.x) {
                 const int u = i >> 2, qq = i & 3;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (u < avail) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)u * kD) + qq);
-                *reinterpret_cast<float4*>(Xs + u * kXS + 4 * qq) = v;
+                *reinterpret_cast<float4*>(Xh + u * kXS + 4 * qq) = v;
             }
         } else {   // mfcc_size < 16: zero-padded to 16
             const float* src = a.frames + (b * a.frame_rows + row0) * a.d;
             for (int i = tid; i < x_rows * kD; i += blockDim.x) {
                 const int u = i >> 4, qq = i & 15;
-                Xs[u * kXS + qq] = (u < avail && qq < a.d) ? __ldg(src + (size_t)u * a.d + qq) : 0.f;
+                Xh[u * kXS + qq] = (u < avail && qq < a.d) ? __ldg(src + (size_t)u * a.d + qq) : 0.f;
             }
         }
     }
     __syncthreads();
 
-    float* Mu = MuAll + warp * (NWIN * kD);
-    float* Inv = InvAll + (size_t)warp * NWIN * inv_cols;
+    const int64_t b = 2 * pair + half;                          // this half-warp's stream
+    const float* Xs = XsAll + (size_t)half * x_rows * kXS;
+    float* Mu = MuAll + (size_t)(warp * 2 + half) * (NWIN * kD);
+    float* Inv = InvAll + (size_t)(warp * 2 + half) * NWIN * inv_cols;
     const unsigned band_mask = ((1u << (2 * a.band)) - 1u) << (W - a.band);   // cells inside [r-band, r+band-1]
     const bool masked = a.band != W;
 
     for (int s = warp; s < a.n_slots; s += n_warps) {
         const int m = a.slot_len[s];
         const float* trow = tmpl_unit + unit_off[s];           // unit template rows, 16 floats each
-        // ---- window means (normalizer.rs:3-31): lane = (dim, half) sums every second frame of window 0, the other
-        // windows follow by sliding the sum; stored NEGATED for the whole warp
+        // ---- window means (normalizer.rs:3-31): lane hl = coefficient, frames summed in ascending order as the reference
+        // does; windows 1 and 2 follow by sliding the sum; stored NEGATED
         {
-            const int dim = lane & 15, half = lane >> 4;
             float sacc = 0.f;
-            for (int f = half; f < m; f += 2) sacc += Xs[f * kXS + dim];
-            sacc += __shfl_xor_sync(0xffffffffu, sacc, 16);
+            for (int f = 0; f < m; f++) sacc += Xs[f * kXS + hl];
             const float fm = (float)m;
-            float s1 = sacc;
 #pragma unroll
             for (int jj = 0; jj < NWIN; jj++) {
-                if (half == 0) Mu[jj * kD + dim] = -__fdiv_rn(s1, fm);
-                s1 = (s1 - Xs[jj * kXS + dim]) + Xs[(jj + m) * kXS + dim];
+                Mu[jj * kD + hl] = -__fdiv_rn(sacc, fm);
+                sacc = (sacc - Xs[jj * kXS + hl]) + Xs[(jj + m) * kXS + hl];
             }
         }
         __syncwarp();
         // ---- 1 / |x_u - mu_jj| for every column of every window (0 for the zero vector: similarity 0)
         for (int jj = 0; jj < NWIN; jj++) {
             const Row16 nmu = ld_row(Mu + jj * kD);
-            for (int c = 1 + lane; c < inv_cols; c += 32) {     // column c <-> tile row jj + c - 1
+            for (int c = 1 + hl; c < inv_cols; c += 16) {       // column c <-> tile row jj + c - 1
                 const Row16 x = ld_row(Xs + (jj + c - 1) * kXS);
                 f2 nn = 0ull;
 #pragma unroll
@@ -155,8 +160,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32) dtw_windows_cadence_kernel(Dtw
         __syncwarp();
 
         // ---- lane roles of the row loop
-        const int wj = lane >= 16 ? min(lane - 16, NWIN - 1) : 0;       // DP lanes: their window
-        const bool is_a = lane >= 12 && lane < 12 + NWIN;                // A lanes: dot with the (negated) mean of window lane - 12
+        const int wj = min(hl, NWIN - 1);                        // DP lanes (hl < NWIN): their window
+        const bool is_a = hl >= 12 && hl < 12 + NWIN;            // A lanes: dot with the (negated) mean of window hl - 12
         const float* Invw = Inv + wj * inv_cols;
         float D[NB], inv[NB];
 #pragma unroll
@@ -177,17 +182,18 @@ __global__ void __launch_bounds__(kMaxWarps * 32) dtw_windows_cadence_kernel(Dtw
                 if (r <= last_row) {                             // warp-uniform
                     const Row16 ar = ar_next;
                     if (r < last_row) ar_next = ld_row(trow + (size_t)r * kD);   // one row ahead (L2)
-                    // one dot per lane: frame u = r - W - 1 + lane of the tile (lanes 0 .. NB+1), or the window's negated mean
-                    const int u = r - W - 1 + lane;
-                    const float* vp = is_a ? Mu + (lane - 12) * kD : Xs + min(max(u, 0), x_rows - 1) * kXS;
+                    // one dot per lane: frame u = r - W - 1 + hl of the stream's tile (lanes 0 .. NB+1 of the half), or the
+                    // window's negated mean
+                    const int u = r - W - 1 + hl;
+                    const float* vp = is_a ? Mu + (hl - 12) * kD : Xs + min(max(u, 0), x_rows - 1) * kXS;
                     float g = dot16(ar, ld_row(vp));
                     if (!is_a && u < 0) g = 0.f;
-                    // the DP lanes fetch A (negated mean: A = -dot) and their ten G values
-                    const float A = -__shfl_sync(0xffffffffu, g, 12 + wj);
+                    // the DP lanes fetch A (negated mean: A = -dot) and their ten G values from their own half
+                    const float A = -__shfl_sync(0xffffffffu, g, hbase + 12 + wj);
                     inv[(k + W) % NB] = Invw[min(r + W - 1, inv_cols - 1)];   // column r+W-1 enters the band
                     float gv[NB];
 #pragma unroll
-                    for (int i = 0; i < NB; i++) gv[i] = __shfl_sync(0xffffffffu, g, wj + i);
+                    for (int i = 0; i < NB; i++) gv[i] = __shfl_sync(0xffffffffu, g, hbase + wj + i);
                     if (r == 1) {
                         // row 1: columns c < 1 must stay +inf (they would otherwise inherit D[0][0])
 #pragma unroll
@@ -210,12 +216,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32) dtw_windows_cadence_kernel(Dtw
                 }
             }
         }
-        if (lane >= 16 && lane - 16 < n_win) {
+        if (hl < n_win && b < a.n_streams) {
             // D[m-1][m] = band offset W+1 of row m-1 (dtw.rs:101); m == 1 has no such cell -> +inf
             const float cost = m >= 2 ? D[W + 1] : INFINITY;
             const float normalized = __fdiv_rn(cost, (float)(2 * m));
             const float score = __fdiv_rn(1.f, 1.f + expf(__fdiv_rn(normalized - a.score_ref, a.score_ref)));
-            a.scores[(b * a.n_new + (j0 + lane - 16)) * a.n_slots + s] = score;
+            a.scores[(b * a.n_new + (j0 + hl)) * a.n_slots + s] = score;
         }
         __syncwarp();   // Mu / Inv are rewritten for the warp's next slot
     }
@@ -234,12 +240,12 @@ cudaError_t launch_dtw_windows_cadence(const DtwWindowsArgs& a, const float* tmp
     const int n = a.n_new - a.first_window;
     if (n <= 0 || a.n_streams <= 0 || a.n_slots <= 0) return cudaSuccess;
     const int triples = (n + NWIN - 1) / NWIN;
-    const int64_t ctas = a.n_streams * (int64_t)triples;
+    const int64_t ctas = ((a.n_streams + 1) / 2) * (int64_t)triples;
     if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
     const int n_warps = a.n_slots < kMaxWarps ? a.n_slots : kMaxWarps;
     const int x_rows = NWIN + a.max_len + W + 1;
     const int inv_cols = a.max_len + W + 1;
-    const size_t bytes = ((size_t)x_rows * kXS + (size_t)n_warps * NWIN * kD + (size_t)n_warps * NWIN * inv_cols) * sizeof(float);
+    const size_t bytes = ((size_t)2 * x_rows * kXS + (size_t)n_warps * 2 * NWIN * kD + (size_t)n_warps * 2 * NWIN * inv_cols) * sizeof(float);
     if (bytes > 200 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(dtw_windows_cadence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
