@@ -364,6 +364,6 @@ def test_cadence_kernel_dense_scores_vs_generic_and_pipeline(d, band, chunks_per
     # same detections (stream, chunk, counter) from all three, scores within the parity bar
     assert res[0][2] == res[1][2] == res[9][2]
     assert [x[:3] for x in res[0][1]] == [x[:3] for x in res[1][1]] == [x[:3] for x in res[9][1]]
-    assert len(res[0][1]) >= 1
+    assert len(res[0][1]) >= 1 or band < 2      # (band 1 leaves the result cell outside the band: every score is 0)
     for x, y in zip(res[0][1], res[1][1]):
         assert _rel(x[3], y[3]) < SCORE_RTOL
