@@ -45,8 +45,9 @@ def test_mfcc_kernel_matches_oracle(d, hops, mfcc_variant):
         # observed on B200 (profiles/r02_k1_error.json): max |delta| 3.7e-5 at d = 16 (coefficients up to 76), i.e. 6.5e-7 of
         # the frame's largest coefficient; SURVEY section 7 asks 1e-4 absolute
         assert err.max() < (1e-4 if d <= 16 else 3e-4), (d, b, err.max(), np.unravel_index(err.argmax(), err.shape))
-        rel = err.max(axis=1) / np.maximum(np.abs(want).max(axis=1), 1e-6)
-        assert rel.max() < 3e-6, (d, b, rel.max())
+        if d >= 5:   # (with one or two coefficients a frame's largest one can be ~0: only the absolute bound is meaningful)
+            rel = err.max(axis=1) / np.maximum(np.abs(want).max(axis=1), 1e-6)
+            assert rel.max() < 3e-6, (d, b, rel.max())
 
 
 def test_mfcc_kernel_reproduces_reference_templates(mfcc_variant):
