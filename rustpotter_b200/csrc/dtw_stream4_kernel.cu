@@ -66,6 +66,24 @@ constexpr int BAR_FULL = 1, BAR_EMPTY = 5, BAR_CONSUMERS = 9, BAR_GROUP = 10;   
 
 typedef unsigned long long f2;
 
+// Phase accounting for tools/profile_k2s_phases.cu (never defined in the library build): cycles per warp role and phase.
+#ifdef RP_K2S_PROFILE
+__device__ unsigned long long g_prof[8][8];
+__shared__ unsigned s_prof[8][8];   // per CTA; lane 0 of warp w owns row w; flushed once at the end of the kernel
+#define PROF_NOW(x) unsigned x; asm volatile("mov.u32 %0, %%clock;" : "=r"(x) :: "memory")
+// ... ordered after the computation of `var` (the compiler is otherwise free to move arithmetic across a clock read)
+#define PROF_NOW_AFTER(x, var) unsigned x; asm volatile("mov.u32 %0, %%clock;" : "=r"(x), "+f"(var) :: "memory")
+#define PROF_ADD(w, k, t0, t1) do { if ((threadIdx.x & 31) == 0) s_prof[w][k] += (unsigned)max((int)((t1) - (t0)), 0) >> 4; } while (0)
+#define PROF_INC(w, k) do { if ((threadIdx.x & 31) == 0) s_prof[w][k] += 1u; } while (0)
+#define PROF_FLUSH(w) do { if ((threadIdx.x & 31) == 0) for (int k_ = 0; k_ < 8; k_++) atomicAdd(&g_prof[w][k_], (unsigned long long)s_prof[w][k_]); } while (0)
+#else
+#define PROF_NOW(x)
+#define PROF_NOW_AFTER(x, var)
+#define PROF_ADD(w, k, t0, t1)
+#define PROF_INC(w, k)
+#define PROF_FLUSH(w)
+#endif
+
 __device__ __forceinline__ f2 pk(float lo, float hi) {
     f2 r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -295,7 +313,10 @@ __device__ __forceinline__ void consumer_loop(const DtwPairsArgs& a, int64_t n_g
     float* const xdrain_w = reinterpret_cast<float*>(sm + dw_o);
     const float* const xdrain_r = reinterpret_cast<const float*>(sm + dr_o);
 
+    // (Rotating the warps' roles from group to group, so that the longest chain of blocks -- warp 0's, 84 of a group's 84
+    // steps against 66-72 -- visits every scheduler, was measured: no change, profiles/r02_k2s_phases.txt.)
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        PROF_NOW(pg0);
         const int64_t p = grp * PPG + lane;
         const bool valid = p < a.n_pairs;
         const int64_t pc = valid ? p : a.n_pairs - 1;                       // clamped: every lane computes on real data
@@ -329,8 +350,16 @@ __device__ __forceinline__ void consumer_loop(const DtwPairsArgs& a, int64_t n_g
         if (0 <= g.n_super - 1 - DEPTH) bar_arrive(BAR_EMPTY);   // super-step 0 is over (nothing was read)
 
         unsigned ctl_next = sched.ctl[wid][1];
+        PROF_NOW(pg1);
+        PROF_ADD(wid, 0, pg0, pg1);   // prologue
         for (int S = 1; S <= g.n_super; S++) {
+            PROF_NOW_AFTER(pw0, out1);
             bar_sync(BAR_FULL + ((S - 1) & 3));   // batch S-1 of the producers, and the neighbours' boundary values
+#ifdef RP_K2S_PROFILE
+            float probe = *reinterpret_cast<const volatile float*>(xdrain_r);   // BAR.SYNC defers blocking to the next memory access
+#endif
+            PROF_NOW_AFTER(pw1, probe);
+            PROF_ADD(wid, 1, pw0, pw1);   // waiting at the super-step barrier
 #pragma unroll 1
             for (int st = 2 * S - 1; st <= min(2 * S, steps); st++) {
                 const unsigned ctl = ctl_next;
@@ -385,11 +414,15 @@ __device__ __forceinline__ void consumer_loop(const DtwPairsArgs& a, int64_t n_g
                     li1_prev = INFINITY;
                     ok2_prev = false;
                 }
+                PROF_INC(wid, 3);
             }
+            PROF_NOW_AFTER(ps1, out1);
+            PROF_ADD(wid, 2, pw1, ps1);   // the super-step's (up to) two steps
             // this super-step's ring and stage reads are over (batch S+DEPTH waits for it, if there is one)
             if (S <= g.n_super - 1 - DEPTH) bar_arrive(BAR_EMPTY + (S & 3));
         }
 
+        PROF_NOW(pe0);
         // ---- result: the warp that owns the last block
         // the group's reads of the ring are over: the producers may store the next group's first batches
         if (grp + gridDim.x < n_groups) bar_arrive(BAR_GROUP);
@@ -423,7 +456,11 @@ __device__ __forceinline__ void consumer_loop(const DtwPairsArgs& a, int64_t n_g
                 a.out[p] = __fdiv_rn(1.f, 1.f + expf(__fdiv_rn(normalized - a.score_ref, a.score_ref)));
             }
         }
+        PROF_NOW(pe1);
+        PROF_ADD(wid, 4, pe0, pe1);   // epilogue
+        PROF_ADD(wid, 5, pg0, pe1);   // whole group
     }
+    PROF_FLUSH(wid);
 }
 
 // ------------------------------------------------------------------------------------------------ producers
@@ -484,20 +521,29 @@ __device__ __forceinline__ void producer_loop(const DtwPairsArgs& a, int64_t n_g
             }
             // the slots this batch overwrites were last read in super-step c-DEPTH at the latest (Stream4Sched invariant),
             // or by the previous group
+            PROF_NOW(pp0);
             if (c >= DEPTH) bar_sync(BAR_EMPTY + ((c - DEPTH) & 3));
             else if (c == 0 && grp != (int64_t)blockIdx.x) bar_sync(BAR_GROUP);
+            PROF_NOW(pp1);
 #pragma unroll
             for (int i = 0; i < 4; i++)
                 if (sched.unit[c][i]) norm_store(v[i][0], v[i][1], dst[i], sign[i], true);   // uniform; the shuffle inside needs every lane
             __threadfence_block();
             bar_arrive(BAR_FULL + (c & 3));
+            PROF_NOW(pp2);
+            PROF_ADD(4 + (tid >> 5), 1, pp0, pp1);   // waiting for free slots
+            PROF_ADD(4 + (tid >> 5), 2, pp1, pp2);   // waiting for the loads + scale + store
         }
     }
+    PROF_FLUSH(4 + (tid >> 5));
 }
 
 __global__ void __launch_bounds__(NTHREADS, 2) dtw_pairs_stream4_kernel(DtwPairsArgs a, int64_t n_groups, int window, Stream4Sched sched) {
     extern __shared__ __align__(16) float smem[];
     for (int i = threadIdx.x; i < SMEM_FLOATS; i += NTHREADS) smem[i] = 0.f;
+#ifdef RP_K2S_PROFILE
+    if (threadIdx.x < 64) (&s_prof[0][0])[threadIdx.x] = 0u;
+#endif
     __syncthreads();
     const Geometry g = make_geometry(a, window);
     if (threadIdx.x >= NW * 32) {

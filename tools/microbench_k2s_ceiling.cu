@@ -54,6 +54,168 @@ __global__ void __launch_bounds__(WARPS * 32) k_full_block(long long* cyc, float
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+
+// The same body with the kernel's per-step surroundings added one at a time (MODE bits): 1 = band masks (the !full path),
+// 2 = control word + boundary exchange through shared memory, 4 = the consumers' named barrier every two steps,
+// 8 = four producer-like warps (32-byte load, norm, store per thread and batch) on a 256-thread full/empty barrier pair.
+__constant__ unsigned c_ctl[256];
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) k_full_block_x(long long* cyc, float* sink, const float* __restrict__ in) {
+    extern __shared__ __align__(16) float smem[];
+    float* ring = smem;
+    float* xch = smem + 32 * RING_PAIR_F;            // [4 warps][4 slots][2][32]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 32 * RING_PAIR_F + 4 * 4 * 2 * 32 + 128; i += blockDim.x) smem[i] = 0.25f * __sinf(0.37f * (float)(i + 7 * blockIdx.x));
+    __syncthreads();
+    if (warp >= 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS));
+        if (!(MODE & 8)) return;
+        // producer-like: per batch (= two consumer steps) four 32-byte units per thread: load (L2-resident), norm, store.
+        // MODE 16: the barrier protocol without the work; MODE 32: the work without the barrier protocol (free-running)
+        const int tid = threadIdx.x - 128;
+        float* dst = ring + (tid >> 2) * RING_PAIR_F + (tid & 3) * 8;
+        const float* src = in + (tid & 63) * 32;   // (a 128-byte stride per lane: 32 lines per load instruction, far worse than the kernel's)
+        if (MODE & 8192) {
+            // pattern B: eight lanes per 128-byte unit -> every 16-byte load instruction covers four whole lines; the vector norm
+            // takes two shuffles; lane l: pair 8w + (l >> 3) in the first load, + 4 in the second, bytes 16 (l & 7) of the unit
+            const int l = tid & 31, w = tid >> 5;
+            const float* qb = in + (8 * w + (l >> 3)) * 1920 + (l & 7) * 4;
+            float* db = ring + (8 * w + (l >> 3)) * RING_PAIR_F + (l & 7) * 4;
+            for (int c = 0; c < STEPS / 2; c++) {
+                ulonglong2 v[4][2];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float* q = qb + ((c * 4 + i) & 15) * 32;
+                    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v[i][0].x), "=l"(v[i][0].y) : "l"(q));
+                    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v[i][1].x), "=l"(v[i][1].y) : "l"(q + 4 * 1920));
+                }
+                if (c >= 2) bar_sync(BAR_EMPTY + ((c - 2) & 3));
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    float* d2 = db + ((c * 4 + i) & 15) * SLOT_F;
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const ulonglong2 x = v[i][h];
+                        float part = hsum(fma2(x.y, x.y, mul2(x.x, x.x)));
+                        part += __shfl_xor_sync(0xffffffffu, part, 1);
+                        part += __shfl_xor_sync(0xffffffffu, part, 2);
+                        const float sc = part > 0.f ? rsqrtf(part) : 0.f;
+                        const f2 s2 = pk(sc, sc);
+                        ulonglong2 o;
+                        o.x = mul2(x.x, s2);
+                        o.y = mul2(x.y, s2);
+                        *reinterpret_cast<ulonglong2*>(d2 + h * 4 * RING_PAIR_F) = o;
+                    }
+                }
+                __threadfence_block();
+                bar_arrive(BAR_FULL + (c & 3));
+            }
+            return;
+        }
+        if (MODE & 4096) src = in + (tid >> 2) * 1920 + (tid & 3) * 8;   // pattern A: the kernel's (four lanes x 32 bytes per 128-byte unit)
+        for (int c = 0; c < STEPS / 2; c++) {
+            ulonglong2 v[4][2];
+            if (!(MODE & 16)) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (MODE & 64) {   // no global loads: synthetic values
+                        v[i][0] = make_ulonglong2(pk(0.1f * (c + i), 0.2f), pk(0.3f, 0.4f + tid));
+                        v[i][1] = make_ulonglong2(pk(0.5f, 0.6f), pk(0.7f * i, 0.8f));
+                    } else if (MODE & 1024) {   // the same bytes as two fully coalesced 16-byte loads per warp
+                        const float* q = in + ((c + i) & 7) * 1024 + tid * 4;
+                        asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v[i][0].x), "=l"(v[i][0].y) : "l"(q));
+                        asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2+2048];" : "=l"(v[i][1].x), "=l"(v[i][1].y) : "l"(q));
+                    } else if (MODE & 2048) {   // through L1 (allocating)
+                        const float4 a0 = __ldg(reinterpret_cast<const float4*>(src + ((c + i) & 7) * 8));
+                        const float4 a1 = __ldg(reinterpret_cast<const float4*>(src + ((c + i) & 7) * 8 + 4));
+                        v[i][0] = make_ulonglong2(pk(a0.x, a0.y), pk(a0.z, a0.w));
+                        v[i][1] = make_ulonglong2(pk(a1.x, a1.y), pk(a1.z, a1.w));
+                    } else if (MODE & 4096) {
+                        ldg32(src + ((c * 4 + i) & 15) * 32, v[i][0], v[i][1]);
+                    } else {
+                        ldg32(src + ((c + i) & 7) * 8, v[i][0], v[i][1]);
+                    }
+                }
+            }
+            if (!(MODE & 32) && c >= 2) bar_sync(BAR_EMPTY + ((c - 2) & 3));
+            if (!(MODE & 16)) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    float* d2 = dst + ((c * 4 + i) & 15) * SLOT_F;
+                    if (MODE & 512) {   // loads only: nothing stored unless the data is a magic value
+                        if ((v[i][0].x ^ v[i][1].y) == 0x123456789abcdefull) *reinterpret_cast<ulonglong2*>(d2) = v[i][0];
+                    } else if (MODE & 256) {   // raw store: no norm, shuffle, rsqrt
+                        *reinterpret_cast<ulonglong2*>(d2) = v[i][0];
+                        *reinterpret_cast<ulonglong2*>(d2 + 4) = v[i][1];
+                    } else {
+                        norm_store(v[i][0], v[i][1], d2, 1.f, true);
+                    }
+                }
+                if (!(MODE & 128)) __threadfence_block();
+            }
+            if (!(MODE & 32)) bar_arrive(BAR_FULL + (c & 3));
+        }
+        return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS));
+    const float* ring_p = ring + lane * RING_PAIR_F;
+    f2 bcol[CB][8];
+#pragma unroll
+    for (int j = 0; j < CB; j++)
+#pragma unroll
+        for (int q = 0; q < 8; q++) bcol[j][q] = pk(in[(j * 8 + q) * 64 + lane], in[(j * 8 + q) * 64 + 32 + lane]);
+    float D1[CB], D2[CB], cost2[CB];
+#pragma unroll
+    for (int j = 0; j < CB; j++) { D1[j] = 0.f; D2[j] = 0.f; cost2[j] = 1.f; }
+    f2 ar1[8];
+    load_row(ring_p, ar1);
+    float out1 = 0.f, out2 = 0.f, li1_prev = 1.f;
+    const f2 one = pk(1.f, 0.f);
+    float* xw = xch + warp * (4 * 2 * 32) + lane;
+    const float* xr = xch + ((warp + 3) & 3) * (4 * 2 * 32) + lane;
+    const long long t0 = clock64();
+    long long waited = 0;
+#pragma unroll 1
+    for (int S = 0; S < STEPS / 2; S++) {
+        if ((MODE & 8) && !(MODE & 32)) {
+            const long long w0 = clock64();
+            bar_sync(BAR_FULL + (S & 3));
+            waited += clock64() - w0;
+        }
+        else if (MODE & 4) asm volatile("bar.sync %0, %1;" ::"n"(BAR_CONSUMERS), "n"(128) : "memory");
+#pragma unroll 1
+        for (int st = 2 * S; st < 2 * S + 2; st++) {
+            const float* rp0 = ring_p + (st & 15) * SLOT_F;
+            const float* rp1 = ring_p + ((st + 1) & 15) * SLOT_F;
+            float li1 = out1, li2p = out2;
+            unsigned M = 0x3ffu;
+            bool full = !(MODE & 1);
+            if (MODE & 2) {
+                const unsigned ctl = c_ctl[st & 255];
+                const unsigned xo = (ctl >> 22) & 3u;
+                const float xd = xr[4 * 2 * 32 * 0 + 96], x0 = xr[xo * 64], shf1 = xr[xo * 64 + 32];
+                li2p = (ctl & 64u) ? ((ctl & 128u) ? xd : x0) : out2;
+                li1 = (ctl & 16u) ? shf1 : out1;
+                M = (ctl >> 12) & 0x3ffu;
+                full = full && (ctl & 4u);
+            }
+            block_step(rp0, rp1, full, M, li1, li2p, li1_prev, bcol, ar1, D1, D2, cost2, out1, out2, one);
+            li1_prev = li1;
+            if (MODE & 2) {
+                xw[(st & 3) * 64] = out2;
+                xw[(st & 3) * 64 + 32] = out1;
+            }
+        }
+        if ((MODE & 8) && !(MODE & 32) && S < STEPS / 2 - 2) bar_arrive(BAR_EMPTY + (S & 3));
+    }
+    const long long t1 = clock64();
+    float s = out1 + out2;
+#pragma unroll
+    for (int j = 0; j < CB; j++) s += D1[j] + D2[j];
+    if (s == 123.456f) sink[0] = s;
+    if (threadIdx.x == 0) { cyc[blockIdx.x] = t1 - t0; cyc[gridDim.x + blockIdx.x] = waited; }
+}
+
 // Half-width block (4 columns, 64 block registers): what 3-4 consumer warps per scheduler would have to run. Same arithmetic
 // per cell; the row loads now serve half as many cells (8 LDS.128 per 8 cells).
 __device__ __forceinline__ void half_step4(const f2 (&ar)[8], const f2 (&bcol)[4][8], f2 (&acc)[4], const float (&cprev)[4],
@@ -141,8 +303,8 @@ int main() {
     CK(cudaMalloc(&sink, 4));
     float* in;
     {
-        static float h[64 * 64];
-        for (int i = 0; i < 64 * 64; i++) h[i] = -0.25f + 0.5f * (float)((i * 2654435761u) >> 8 & 0xffff) / 65536.f;
+        static float h[20 * 64 * 64];
+        for (int i = 0; i < 20 * 64 * 64; i++) h[i] = -0.25f + 0.5f * (float)((i * 2654435761u) >> 8 & 0xffff) / 65536.f;
         CK(cudaMalloc(&in, sizeof(h)));
         CK(cudaMemcpy(in, h, sizeof(h), cudaMemcpyHostToDevice));
     }
@@ -161,6 +323,61 @@ int main() {
         const double fma_pct = (c.cols * 16.0 * 2.0) / c.cyc * (c.warps * c.ctas / 4.0) * 100.0;   // FFMA2 pipe cycles (2 per FFMA2) per scheduler
         printf("%-70s %7.1f cycles/step/warp  -> %6.3f ms per 1 M pairs (%.2f of the 6547 GB/s roofline), FFMA2 pipe %.0f %%\n", c.name, c.cyc, ms,
                14.084 / ms / 6547.2 * 1e3, fma_pct);
+    }
+    {   // the surroundings of the step, one at a time (8-column block, two CTAs per SM = the kernel's occupancy)
+        unsigned h[256];
+        for (int i = 0; i < 256; i++) h[i] = 1u | 4u | 16u | 64u | (0x3ffu << 12) | ((unsigned)(i & 15) << 22);   // active, full, ok1, ok2prev, all cells in band
+        CK(cudaMemcpyToSymbol(c_ctl, h, sizeof(h)));
+        const size_t smem = (size_t)(32 * RING_PAIR_F + 4 * 4 * 2 * 32 + 128) * sizeof(float);
+        struct V { const char* name; int mode; } vs[] = {{"body only (256-thread CTA, producers exit)", 0}, {"+ band masks", 1}, {"+ control word and boundary exchange", 2},
+            {"+ masks + exchange", 3}, {"+ consumer barrier every two steps", 4 | 2}, {"+ masks + exchange + barrier", 7},
+            {"+ exchange + producers on full/empty barriers", 8 | 2}, {"+ masks + exchange + producers (the kernel's structure, no idle steps)", 8 | 3},
+            {"+ exchange + producers: barrier protocol only, no loads/stores", 8 | 2 | 16},
+            {"+ exchange + producers without the global loads", 8 | 2 | 64}, {"+ exchange + producers without the fence", 8 | 2 | 128},
+            {"+ exchange + producers storing raw data (no norm / shuffle / rsqrt)", 8 | 2 | 256},
+            {"+ exchange + producers: raw stores, no loads, no fence", 8 | 2 | 64 | 128 | 256},
+            {"+ exchange + producers: loads only, nothing stored", 8 | 2 | 512}, {"+ exchange + producers with fully coalesced loads", 8 | 2 | 1024},
+            {"+ exchange + producers loading through L1", 8 | 2 | 2048},
+            {"+ exchange + producers, the kernel's load pattern A (4 lanes x 32 B per unit)", 8 | 2 | 4096},
+            {"+ exchange + producers, load pattern B (8 lanes x 16 B per unit, 2 shuffles)", 8 | 2 | 8192}, {"+ exchange + consumer barrier + free-running producers (work, no full/empty)", 8 | 2 | 4 | 32}};
+        for (auto& v : vs) {
+            auto launch = [&](auto kern) {
+                CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                for (int rep = 0; rep < 2; rep++) {
+                    kern<<<nsm * 2, 256, smem>>>(cyc, sink, in);
+                    CK(cudaDeviceSynchronize());
+                }
+            };
+            switch (v.mode) {
+                case 0: launch(k_full_block_x<0>); break;
+                case 1: launch(k_full_block_x<1>); break;
+                case 2: launch(k_full_block_x<2>); break;
+                case 3: launch(k_full_block_x<3>); break;
+                case 6: launch(k_full_block_x<6>); break;
+                case 7: launch(k_full_block_x<7>); break;
+                case 10: launch(k_full_block_x<10>); break;
+                case 26: launch(k_full_block_x<26>); break;
+                case 74: launch(k_full_block_x<74>); break;
+                case 138: launch(k_full_block_x<138>); break;
+                case 266: launch(k_full_block_x<266>); break;
+                case 458: launch(k_full_block_x<458>); break;
+                case 522: launch(k_full_block_x<522>); break;
+                case 1034: launch(k_full_block_x<1034>); break;
+                case 2058: launch(k_full_block_x<2058>); break;
+                case 4106: launch(k_full_block_x<4106>); break;
+                case 8202: launch(k_full_block_x<8202>); break;
+                case 46: launch(k_full_block_x<46>); break;
+                default: launch(k_full_block_x<11>); break;
+            }
+            static long long hc[4096];
+            CK(cudaMemcpy(hc, cyc, nsm * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
+            double avg = 0, wavg = 0;
+            for (int i = 0; i < nsm * 2; i++) { avg += (double)hc[i]; wavg += (double)hc[nsm * 2 + i]; }
+            const double c = avg / (nsm * 2) / STEPS;
+            const double ms = 1e6 / 32.0 * 4656.0 / 16.0 * c / ((double)nsm * 8) / (ghz * 1e9) * 1e3;
+            printf("%-75s %7.1f cycles/step/warp (%6.1f waiting for data) -> %6.3f ms per 1 M pairs (%.2f of roofline)\n", v.name, c,
+                   (v.mode & 8) ? wavg / (nsm * 2) / STEPS : 0.0, ms, 14.084 / ms / 6547.2 * 1e3);
+        }
     }
     return 0;
 }
