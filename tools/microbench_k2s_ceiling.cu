@@ -183,6 +183,16 @@ __global__ void __launch_bounds__(256, 2) k_full_block_x(long long* cyc, float* 
             waited += clock64() - w0;
         }
         else if (MODE & 4) asm volatile("bar.sync %0, %1;" ::"n"(BAR_CONSUMERS), "n"(128) : "memory");
+        float px0[2] = {0.f, 0.f}, psh[2] = {0.f, 0.f}, pxd = 0.f;
+        if (MODE & 16384) {   // both steps' boundary values right after the barrier (they were written in the previous super-step)
+            pxd = xr[96];
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const unsigned xo = (c_ctl[(2 * S + k) & 255] >> 22) & 3u;
+                px0[k] = xr[xo * 64];
+                psh[k] = xr[xo * 64 + 32];
+            }
+        }
 #pragma unroll 1
         for (int st = 2 * S; st < 2 * S + 2; st++) {
             const float* rp0 = ring_p + (st & 15) * SLOT_F;
@@ -193,7 +203,16 @@ __global__ void __launch_bounds__(256, 2) k_full_block_x(long long* cyc, float* 
             if (MODE & 2) {
                 const unsigned ctl = c_ctl[st & 255];
                 const unsigned xo = (ctl >> 22) & 3u;
-                const float xd = xr[4 * 2 * 32 * 0 + 96], x0 = xr[xo * 64], shf1 = xr[xo * 64 + 32];
+                float xd, x0, shf1;
+                if (MODE & 16384) {
+                    xd = pxd;
+                    x0 = (st & 1) ? px0[1] : px0[0];
+                    shf1 = (st & 1) ? psh[1] : psh[0];
+                } else {
+                    xd = xr[4 * 2 * 32 * 0 + 96];
+                    x0 = xr[xo * 64];
+                    shf1 = xr[xo * 64 + 32];
+                }
                 li2p = (ctl & 64u) ? ((ctl & 128u) ? xd : x0) : out2;
                 li1 = (ctl & 16u) ? shf1 : out1;
                 M = (ctl >> 12) & 0x3ffu;
@@ -339,7 +358,10 @@ int main() {
             {"+ exchange + producers: loads only, nothing stored", 8 | 2 | 512}, {"+ exchange + producers with fully coalesced loads", 8 | 2 | 1024},
             {"+ exchange + producers loading through L1", 8 | 2 | 2048},
             {"+ exchange + producers, the kernel's load pattern A (4 lanes x 32 B per unit)", 8 | 2 | 4096},
-            {"+ exchange + producers, load pattern B (8 lanes x 16 B per unit, 2 shuffles)", 8 | 2 | 8192}, {"+ exchange + consumer barrier + free-running producers (work, no full/empty)", 8 | 2 | 4 | 32}};
+            {"+ exchange + producers, load pattern B (8 lanes x 16 B per unit, 2 shuffles)", 8 | 2 | 8192},
+            {"+ masks + exchange + producers with pattern A: the kernel's steady state", 8 | 3 | 4096},
+            {"+ exchange, boundary values of both steps loaded at the barrier", 2 | 16384},
+            {"+ masks + exchange (prefetched) + producers with pattern A", 8 | 3 | 4096 | 16384}, {"+ exchange + consumer barrier + free-running producers (work, no full/empty)", 8 | 2 | 4 | 32}};
         for (auto& v : vs) {
             auto launch = [&](auto kern) {
                 CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -366,6 +388,9 @@ int main() {
                 case 2058: launch(k_full_block_x<2058>); break;
                 case 4106: launch(k_full_block_x<4106>); break;
                 case 8202: launch(k_full_block_x<8202>); break;
+                case 4107: launch(k_full_block_x<4107>); break;
+                case 16386: launch(k_full_block_x<16386>); break;
+                case 20491: launch(k_full_block_x<20491>); break;
                 case 46: launch(k_full_block_x<46>); break;
                 default: launch(k_full_block_x<11>); break;
             }
