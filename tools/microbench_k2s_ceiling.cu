@@ -235,6 +235,172 @@ __global__ void __launch_bounds__(256, 2) k_full_block_x(long long* cyc, float* 
     if (threadIdx.x == 0) { cyc[blockIdx.x] = t1 - t0; cyc[gridDim.x + blockIdx.x] = waited; }
 }
 
+// ---- the same step over RAW template rows (no producer-side normalisation): the dots are taken with the raw row and scaled by
+// the row's inverse norm afterwards, cost = 1 + (a . -b^) / |a| (a zero row gives cost 1 = similarity 0).
+__device__ __forceinline__ float row_inv_norm(const f2 (&ar)[8]) {
+    f2 s0 = mul2(ar[0], ar[0]), s1 = mul2(ar[1], ar[1]);
+#pragma unroll
+    for (int q = 2; q < 8; q += 2) {
+        s0 = fma2(ar[q], ar[q], s0);
+        s1 = fma2(ar[q + 1], ar[q + 1], s1);
+    }
+    const float nn = hsum(s0) + hsum(s1);
+    return nn > 0.f ? rsqrtf(nn) : 0.f;
+}
+__device__ __forceinline__ void half_step_raw(const f2 (&ar)[8], const f2 (&bcol)[CB][8], f2 (&acc)[CB], const float (&cprev)[CB],
+                                              const float (&Dsrc)[CB], float (&Ddst)[CB], float left, float diag) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+#pragma unroll
+        for (int j = 0; j < CB; j++) acc[j] = q == 0 ? mul2(ar[0], bcol[j][0]) : fma2(ar[q], bcol[j][q], acc[j]);
+        const float up = Dsrc[q];
+        const float v = cprev[q] + min3(up, diag, left);
+        diag = up;
+        left = v;
+        Ddst[q] = v;
+    }
+}
+// ia1: inverse norm of the look-ahead row in ar1 (in: of row 2u-1, out: of row 2u+1)
+__device__ __forceinline__ void block_step_raw(const float* __restrict__ rp0, const float* __restrict__ rp1, bool full, unsigned M, float li1,
+                                               float li2p, float li1_prev, const f2 (&bcol)[CB][8], f2 (&ar1)[8], float& ia1, float (&D1)[CB],
+                                               float (&D2)[CB], float (&cost2)[CB], float& out1, float& out2) {
+    f2 ar2[8], acc[CB];
+    float cost1[CB];
+    load_row(rp0 + kD, ar2);
+    half_step_raw(ar1, bcol, acc, cost2, D1, D2, li2p, li1_prev);
+    out2 = D2[CB - 1];
+    const float ia2 = row_inv_norm(ar2);
+#pragma unroll
+    for (int j = 0; j < CB; j++) cost1[j] = fmaf(hsum(acc[j]), ia1, 1.f);
+    if (!full) {
+#pragma unroll
+        for (int j = 0; j < CB; j++)
+            if (!((M >> (7 - j)) & 1u)) cost1[j] = INFINITY;
+    }
+    load_row(rp1, ar1);
+    half_step_raw(ar2, bcol, acc, cost1, D2, D1, li1, li2p);
+    out1 = D1[CB - 1];
+    ia1 = row_inv_norm(ar1);
+#pragma unroll
+    for (int j = 0; j < CB; j++) cost2[j] = fmaf(hsum(acc[j]), ia2, 1.f);
+    if (!full) {
+#pragma unroll
+        for (int j = 0; j < CB; j++)
+            if (!((M >> (8 - j)) & 1u)) cost2[j] = INFINITY;
+    }
+}
+
+// A v6 candidate: no producer arithmetic at all. One loader warp (lane = pair) moves RAW rows into the ring with one 512-byte
+// bulk copy per pair and batch (cp.async.bulk, completion counted on an mbarrier the loader itself waits on; the consumers keep
+// the hardware-blocking named barriers), and every consumer scales its dots by the row's inverse norm (block_step_raw: +16
+// FFMA2/FMUL2 and two MUFU per step). CTA = 256 threads as in the kernel (registers are per scheduler: 2 x 200 + 2 x 56), warps
+// 5-7 give their registers back and exit.
+// MODE bits: 1 masks, 2 exchange, 4 the loader issues the copies (else: barrier protocol only), 8 normalised rows (block_step
+// with the loader: what the copies alone cost)
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) k_raw_tma(long long* cyc, float* sink, const float* __restrict__ in) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(8) unsigned long long mbar[4];
+    float* ring = smem;
+    float* xch = smem + 32 * RING_PAIR_F;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 32 * RING_PAIR_F + 4 * 4 * 2 * 32 + 128; i += blockDim.x) smem[i] = 0.25f * __sinf(0.37f * (float)(i + 7 * blockIdx.x));
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&mbar[i])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp >= 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS));
+        if (warp > 4) return;
+        const float* src = in + lane * 1920;
+        const unsigned dst = smem_addr(ring + lane * RING_PAIR_F);
+        for (int c = 0; c < STEPS / 2; c++) {
+            if (c >= 2) asm volatile("bar.sync %0, %1;" ::"r"(BAR_EMPTY + ((c - 2) & 3)), "n"(160) : "memory");
+            if (MODE & 4) {
+                const unsigned bar = smem_addr(&mbar[c & 3]);
+                if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(32 * 512) : "memory");
+                __syncwarp();
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst + ((c * 4) & 15) * SLOT_F * 4), "l"(src + ((c * 4) & 15) * SLOT_F), "r"(512), "r"(bar) : "memory");
+                asm volatile(
+                    "{\n"
+                    ".reg .pred p;\n"
+                    "WAIT_LOOP:\n"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                    "@p bra WAIT_DONE;\n"
+                    "bra WAIT_LOOP;\n"
+                    "WAIT_DONE:\n"
+                    "}\n" ::"r"(bar), "r"((c >> 2) & 1) : "memory");
+            }
+            asm volatile("bar.arrive %0, %1;" ::"r"(BAR_FULL + (c & 3)), "n"(160) : "memory");
+        }
+        return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS));
+    const float* ring_p = ring + lane * RING_PAIR_F;
+    f2 bcol[CB][8];
+#pragma unroll
+    for (int j = 0; j < CB; j++)
+#pragma unroll
+        for (int q = 0; q < 8; q++) bcol[j][q] = pk(in[(j * 8 + q) * 64 + lane], in[(j * 8 + q) * 64 + 32 + lane]);
+    float D1[CB], D2[CB], cost2[CB];
+#pragma unroll
+    for (int j = 0; j < CB; j++) { D1[j] = 0.f; D2[j] = 0.f; cost2[j] = 1.f; }
+    f2 ar1[8];
+    load_row(ring_p, ar1);
+    float ia1 = row_inv_norm(ar1);
+    float out1 = 0.f, out2 = 0.f, li1_prev = 1.f;
+    const f2 one = pk(1.f, 0.f);
+    float* xw = xch + warp * (4 * 2 * 32) + lane;
+    const float* xr = xch + ((warp + 3) & 3) * (4 * 2 * 32) + lane;
+    const long long t0 = clock64();
+    long long waited = 0;
+#pragma unroll 1
+    for (int S = 0; S < STEPS / 2; S++) {
+        {
+            const long long w0 = clock64();
+            asm volatile("bar.sync %0, %1;" ::"r"(BAR_FULL + (S & 3)), "n"(160) : "memory");
+            const float probe = *reinterpret_cast<const volatile float*>(xr + 96);
+            long long w1;
+            asm volatile("mov.u64 %0, %%clock64;" : "=l"(w1), "+f"(out1) : "f"(probe) : "memory");
+            waited += w1 - w0;
+        }
+#pragma unroll 1
+        for (int st = 2 * S; st < 2 * S + 2; st++) {
+            const float* rp0 = ring_p + (st & 15) * SLOT_F;
+            const float* rp1 = ring_p + ((st + 1) & 15) * SLOT_F;
+            float li1 = out1, li2p = out2;
+            unsigned M = 0x3ffu;
+            bool full = !(MODE & 1);
+            if (MODE & 2) {
+                const unsigned ctl = c_ctl[st & 255];
+                const unsigned xo = (ctl >> 22) & 3u;
+                const float xd = xr[96], x0 = xr[xo * 64], shf1 = xr[xo * 64 + 32];
+                li2p = (ctl & 64u) ? ((ctl & 128u) ? xd : x0) : out2;
+                li1 = (ctl & 16u) ? shf1 : out1;
+                M = (ctl >> 12) & 0x3ffu;
+                full = full && (ctl & 4u);
+            }
+            if (MODE & 8) block_step(rp0, rp1, full, M, li1, li2p, li1_prev, bcol, ar1, D1, D2, cost2, out1, out2, one);
+            else block_step_raw(rp0, rp1, full, M, li1, li2p, li1_prev, bcol, ar1, ia1, D1, D2, cost2, out1, out2);
+            li1_prev = li1;
+            if (MODE & 2) {
+                xw[(st & 3) * 64] = out2;
+                xw[(st & 3) * 64 + 32] = out1;
+            }
+        }
+        if (S < STEPS / 2 - 2) asm volatile("bar.arrive %0, %1;" ::"r"(BAR_EMPTY + (S & 3)), "n"(160) : "memory");
+    }
+    const long long t1 = clock64();
+    float s = out1 + out2 + ia1;
+#pragma unroll
+    for (int j = 0; j < CB; j++) s += D1[j] + D2[j];
+    if (s == 123.456f) sink[0] = s;
+    if (threadIdx.x == 0) { cyc[blockIdx.x] = t1 - t0; cyc[gridDim.x + blockIdx.x] = waited; }
+}
+
 // Half-width block (4 columns, 64 block registers): what 3-4 consumer warps per scheduler would have to run. Same arithmetic
 // per cell; the row loads now serve half as many cells (8 LDS.128 per 8 cells).
 __device__ __forceinline__ void half_step4(const f2 (&ar)[8], const f2 (&bcol)[4][8], f2 (&acc)[4], const float (&cprev)[4],
@@ -402,6 +568,36 @@ int main() {
             const double ms = 1e6 / 32.0 * 4656.0 / 16.0 * c / ((double)nsm * 8) / (ghz * 1e9) * 1e3;
             printf("%-75s %7.1f cycles/step/warp (%6.1f waiting for data) -> %6.3f ms per 1 M pairs (%.2f of roofline)\n", v.name, c,
                    (v.mode & 8) ? wavg / (nsm * 2) / STEPS : 0.0, ms, 14.084 / ms / 6547.2 * 1e3);
+        }
+    }
+    {   // v6 candidate: raw rows by bulk copy, inverse norms in the consumers
+        const size_t smem = (size_t)(32 * RING_PAIR_F + 4 * 4 * 2 * 32 + 128) * sizeof(float);
+        struct V { const char* name; int mode; } vs[] = {{"raw-row body + exchange, loader warp: barrier protocol only", 2}, {"raw-row body + exchange + masks, barrier protocol only", 3},
+            {"raw-row body + exchange + 512-byte bulk copies per pair and batch", 2 | 4}, {"raw-row body + exchange + masks + bulk copies: the v6 steady state", 3 | 4},
+            {"normalised-row body + exchange + masks + bulk copies (what the copies cost)", 3 | 4 | 8}};
+        for (auto& v : vs) {
+            auto launch = [&](auto kern) {
+                CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                for (int rep = 0; rep < 2; rep++) {
+                    kern<<<nsm * 2, 256, smem>>>(cyc, sink, in);
+                    CK(cudaDeviceSynchronize());
+                }
+            };
+            switch (v.mode) {
+                case 2: launch(k_raw_tma<2>); break;
+                case 3: launch(k_raw_tma<3>); break;
+                case 6: launch(k_raw_tma<6>); break;
+                case 7: launch(k_raw_tma<7>); break;
+                default: launch(k_raw_tma<15>); break;
+            }
+            static long long hc[4096];
+            CK(cudaMemcpy(hc, cyc, nsm * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
+            double avg = 0, wavg = 0;
+            for (int i = 0; i < nsm * 2; i++) { avg += (double)hc[i]; wavg += (double)hc[nsm * 2 + i]; }
+            const double c = avg / (nsm * 2) / STEPS;
+            const double ms = 1e6 / 32.0 * 4656.0 / 16.0 * c / ((double)nsm * 8) / (ghz * 1e9) * 1e3;
+            printf("%-75s %7.1f cycles/step/warp (%6.1f waiting for data) -> %6.3f ms per 1 M pairs (%.2f of roofline)\n", v.name, c,
+                   wavg / (nsm * 2) / STEPS, ms, 14.084 / ms / 6547.2 * 1e3);
         }
     }
     return 0;
