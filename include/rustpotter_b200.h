@@ -229,11 +229,9 @@ int rp_dtw_scores(const float* tmpl_dev, const int64_t* tmpl_off_dev, const int3
                   const float* win_dev, const int64_t* win_off_dev, const int32_t* win_len_dev, int win_len_uniform,
                   int64_t n_pairs, int d, int band, float score_ref, int cmn, float* out_dev, void* cuda_stream);
 /* Selects the DTW kernel variants (process-wide debug knob for A/B measurements and parity tests): 0 = automatic,
- * 1 = generic reference-order kernels, 2 = tuned kernels, 6 = tuned with the v3 streaming kernel (lanes of a pair as the
- * systolic array) even where v4 (warps of a CTA as the systolic array, producer/consumer warpgroups; windows 3..20)
- * applies, 7 = tuned with the pipeline kernel reading its templates from shared instead of constant memory, 9 = tuned with the
- * pipeline kernel also for short calls (instead of the warp-per-window-triple cadence kernel); 3, 4 and 5 (retired
- * round-1 variants) behave like 2. */
+ * 1 = generic reference-order kernels, 2 = tuned kernels, 7 = tuned with the pipeline kernel reading its templates from
+ * shared instead of constant memory, 9 = tuned with the pipeline kernel also for short calls (instead of the cadence
+ * kernel); 3, 4, 5 and 6 (retired variants) behave like 2. */
 int rp_set_dtw_variant(int variant);
 /* Avg gate of the batched window scorer: 1 / -1 (default) = score avg_features first and the templates only where the
  * gate can pass, as the reference does; 0 = every template of every window (dense score tensor; parity taps, A/B). The

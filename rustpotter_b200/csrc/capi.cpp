@@ -708,11 +708,9 @@ int rp_dtw_scores(const float* tmpl_dev, const int64_t* tmpl_off_dev, const int3
 }
 
 int rp_set_dtw_variant(int v) {
-    // 0 automatic, 1 generic kernels, 2 tuned kernels, 6 tuned with the v3 streaming kernel (lanes of a pair as the systolic
-    // array) even where v4 applies, 7 tuned with the pipeline kernel reading its templates from shared instead of constant
-    // memory; 3, 4, 5 (retired round-1 variants) behave like 2. Alternatives kept for A/B measurements and parity tests.
+    // 0 automatic, 1 generic kernels, 2 tuned kernels, 7 tuned with the pipeline kernel reading its templates from shared
+    // instead of constant memory; 3..6 (retired variants) behave like 2. Alternatives kept for A/B measurements and parity tests.
     g_dtw_variant.store(v == 9 ? 9 : (v >= 3 ? 2 : v));   // 9: tuned, but the pipeline kernel also for short calls (no cadence kernel)
-    set_dtw_stream_rows(v == 6 ? 3 : 0);
     set_dtw_window_kernel(v == 7 ? 3 : 0);
     return RP_OK;
 }

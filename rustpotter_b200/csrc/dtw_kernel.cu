@@ -10,7 +10,7 @@
 // k-1 and k-2). It evaluates every floating-point operation in the reference's order with explicit
 // round-to-nearest mul/add (no FMA contraction), so its costs are bit-identical to the reference's
 // f32 arithmetic; only the final expf may differ in the last ulp. The tuned kernels
-// (dtw_stream3/4_kernel.cu, dtw_window_kernel.cu) are validated against it and the oracle.
+// (dtw_stream4_kernel.cu, dtw_window_kernel.cu, dtw_cadence_kernel.cu) are validated against it and the oracle.
 //
 // Reference quirks reproduced:
 //   - a = template (m rows), b = window (n cols); window = max(band, |m-n|)

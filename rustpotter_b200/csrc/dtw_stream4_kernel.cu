@@ -4,7 +4,7 @@
 // asymmetric band [r-w, r+w-1], result cell D[m-1][n], cosine distance with similarity 0 for zero
 // vectors, cost/(m+n) -> logistic score).
 //
-// Same arithmetic as dtw_stream3_kernel.cu (a block of 8 window columns lives in registers as negated
+// Same arithmetic as the retired v3 kernel (a block of 8 window columns lives in registers as negated
 // unit vectors, the template streams past it two rows per step, FFMA2 dots with the DP chain of the
 // previous row interleaved), but the systolic array is turned by 90 degrees and the CTA is split in roles:
 //
@@ -376,7 +376,8 @@ __device__ __forceinline__ void consumer_loop(const DtwPairsArgs& a, int64_t n_g
                 // D[2u-2][c0-1]: the left block's H1 of row pair u, or its drain if row pair u-1 was its last (block 0 reads
                 // the last warp's values and ignores them)
                 const float* x = reinterpret_cast<const float*>(reinterpret_cast<const char*>(xch_r) + xo);
-                const float xd = xdrain_r[0], x0 = x[0], shf1 = x[32];
+                // (the drain slot is read only in the step that uses it: its owner may be rewriting it in any other step)
+                const float xd = (ctl & CTL_DRAIN_RD) ? xdrain_r[0] : 0.f, x0 = x[0], shf1 = x[32];
                 const float shf2 = (ctl & CTL_DRAIN_RD) ? xd : x0;
                 const float li2p = ok2_prev ? shf2 : dseed;              // left input of row 2u-2 = diagonal input of row 2u-1
                 const float li1 = (ctl & CTL_OK1) ? shf1 : INFINITY;     // left input of row 2u-1 = diagonal input of row 2u

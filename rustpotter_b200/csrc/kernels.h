@@ -54,11 +54,10 @@ struct DtwPairsArgs {
 };
 // K2 generic ("faithful") kernel: one warp per pair, anti-diagonal wavefront, reference operation order.
 cudaError_t launch_dtw_pairs_generic(const DtwPairsArgs& a, cudaStream_t stream);
-// K2s streaming kernels for independent pairs (dtw_pairs_dispatch.cu picks v4 or v3): d == 16, uniform lengths, no CMN,
-// window = max(band, |m-n|) <= 20.
+// K2s streaming kernel for independent pairs (dtw_pairs_dispatch.cu): d == 16, uniform lengths, no CMN,
+// window = max(band, |m-n|) in 3..20, at most 238 steps.
 bool dtw_pairs_stream_supported(const DtwPairsArgs& a);
 cudaError_t launch_dtw_pairs_stream(const DtwPairsArgs& a, cudaStream_t stream);
-void set_dtw_stream_rows(int v);   // 0 = newest kernel that takes the shape, 3 = v3 (debug / A-B)
 // K2s v4 (dtw_stream4_kernel.cu): what its producer warps fetch in which batch; built on the host per (m, n, band).
 constexpr int STREAM4_MAX_BATCHES = 120;
 constexpr int STREAM4_MAX_STEPS = 2 * STREAM4_MAX_BATCHES;

@@ -129,8 +129,7 @@ def test_dtw_kernel_matches_oracle(m, n, d, band, cmn):
         ref.append(O.compare(a[p], wb, band, 0.22))
     # variant 1 = generic kernel (reference operation order, held to 5e-6); 0 = automatic choice
     # (streaming kernel where it applies; FFMA2 dots + rsqrt change the rounding, held to 3e-5)
-    # 6 = the v3 half-step kernel (0 prefers the v4 warp-per-block kernel for windows 3..20, then v3 for windows <= 20)
-    for variant, tol in ((1, 5e-6), (0, 3e-5), (6, 3e-5)):
+    for variant, tol in ((1, 5e-6), (0, 3e-5)):
         rp.set_dtw_variant(variant)
         got = rp.dtw_scores(torch.from_numpy(a).cuda(), torch.from_numpy(w).cuda(), band=band, cmn=cmn).cpu().numpy()
         rp.set_dtw_variant(0)
@@ -152,12 +151,10 @@ def test_dtw_stream_kernel_many_pairs_vs_generic():
     w = torch.randn((P, 100, 16), device="cuda", generator=g) * scale
     rp.set_dtw_variant(1)
     ref = rp.dtw_scores(a, w, band=5)
-    for variant in (0, 6):
-        rp.set_dtw_variant(variant)
-        got = rp.dtw_scores(a, w, band=5)
-        rp.set_dtw_variant(0)
-        rel = ((got - ref).abs() / ref.abs().clamp_min(1e-12)).max().item()
-        assert rel < 3e-5, (variant, rel)
+    rp.set_dtw_variant(0)
+    got = rp.dtw_scores(a, w, band=5)
+    rel = ((got - ref).abs() / ref.abs().clamp_min(1e-12)).max().item()
+    assert rel < 3e-5, rel
     assert float(ref.min()) > 0
 
 
@@ -189,9 +186,9 @@ def test_dtw_stream4_shape_sweep_vs_generic(band):
         assert rel.numel() == 0 or rel.max().item() < 3e-5, (m, n, band, rel.max().item(), int(rel.argmax()))
 
 
-def test_dtw_stream_kernels_with_pair_offsets():
+def test_dtw_stream_kernel_with_pair_offsets():
     """Uniform lengths but per-pair offsets (pairs share and permute their templates and windows): the streaming kernels
-    take this form too (variant 0 -> v4, 6 -> v3); same scores as the dense layout in the permuted order."""
+    takes this form too; same scores as the dense layout in the permuted order."""
     torch = _torch()
     P, m, n, d = 333, 104, 96, 16
     g = torch.Generator(device="cuda").manual_seed(77)
@@ -201,20 +198,18 @@ def test_dtw_stream_kernels_with_pair_offsets():
     perm_w = (torch.arange(P, device="cuda") * 7) % P          # windows reused in another order
     rp.set_dtw_variant(1)
     ref = rp.dtw_scores(a[perm_a].contiguous(), w[perm_w].contiguous(), band=9)
-    for variant in (0, 6):
-        rp.set_dtw_variant(variant)
-        got = rp.dtw_scores(a.reshape(-1), w.reshape(-1), band=9, tmpl_off=(perm_a * (m * d)).to(torch.int64),
-                            win_off=(perm_w * (n * d)).to(torch.int64), max_tmpl_len=m, max_win_len=n, d=d, n_pairs=P)
-        rp.set_dtw_variant(0)
-        rel = ((got - ref).abs() / ref.abs().clamp_min(1e-12)).max().item()
-        assert rel < 3e-5, (variant, rel)
+    rp.set_dtw_variant(0)
+    got = rp.dtw_scores(a.reshape(-1), w.reshape(-1), band=9, tmpl_off=(perm_a * (m * d)).to(torch.int64),
+                        win_off=(perm_w * (n * d)).to(torch.int64), max_tmpl_len=m, max_win_len=n, d=d, n_pairs=P)
+    rel = ((got - ref).abs() / ref.abs().clamp_min(1e-12)).max().item()
+    assert rel < 3e-5, rel
 
 
 def test_dtw_stream4_longest_supported_shape():
     """The v4 kernel's schedule tables hold 238 steps: the longest shapes it takes, and one just beyond (falls back)."""
     torch = _torch()
     g = torch.Generator(device="cuda").manual_seed(78)
-    for m, n in ((320, 312), (322, 312)):   # 238 and 237 steps; longer shapes take v3
+    for m, n in ((320, 312), (322, 312)):   # 238 and 237 steps; longer shapes take the generic kernel
         a = torch.randn((40, m, 16), device="cuda", generator=g)
         w = torch.randn((40, n, 16), device="cuda", generator=g)
         rp.set_dtw_variant(1)

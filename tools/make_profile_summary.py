@@ -1,0 +1,158 @@
+"""Builds profiles/r02_SUMMARY.md from the files committed under profiles/ (bench lines, ncu launch list, ncu raw pages,
+micro-benchmark outputs). Usage: python tools/make_profile_summary.py > profiles/r02_SUMMARY.md"""
+import collections
+import csv
+import json
+import os
+import re
+import sys
+
+P = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles")
+csv.field_size_limit(1 << 30)
+
+
+def load_json_line(name):
+    path = os.path.join(P, name)
+    if not os.path.exists(path):
+        return None
+    for line in open(path):
+        line = line.strip()
+        if line.startswith("{"):
+            try:
+                return json.loads(line)
+            except json.JSONDecodeError:
+                pass
+    return None
+
+
+def short_kernel(name):
+    m = re.search(r"([A-Za-z0-9_]+_kernel[A-Za-z0-9_]*)(<[^>]*>)?", name)
+    if m and ("rp::" in name or "unnamed" in name) and "at::" not in name:
+        return m.group(1) + (m.group(2) or "")
+    return "torch kernels (synthetic workload generation, outside the timed region)"
+
+
+def launch_shares(name):
+    path = os.path.join(P, name)
+    if not os.path.exists(path):
+        return None
+    rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
+    hdr = rows[0]
+    ix = {h: i for i, h in enumerate(hdr)}
+    tot = collections.Counter()
+    cnt = collections.Counter()
+    for r in rows[1:]:
+        if r[ix["Metric Name"]] != "gpu__time_duration.sum":
+            continue
+        v = float(r[ix["Metric Value"]].replace(",", ""))
+        u = r[ix["Metric Unit"]]
+        v *= {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(u, 1e-6)
+        k = short_kernel(r[ix["Kernel Name"]])
+        tot[k] += v
+        cnt[k] += 1
+    return tot, cnt
+
+
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__inst_executed.sum",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
+        "launch__occupancy_limit_shared_mem", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed"]
+
+
+def raw_page(name):
+    path = os.path.join(P, name)
+    if not os.path.exists(path):
+        return None
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    out = []
+    for vals in rows[2:]:
+        kn = vals[hdr.index("Kernel Name")]
+        d = {}
+        for h, u, v in zip(hdr, units, vals):
+            key = h.split(".", 2)[-1] if h.count(".") >= 2 and h.split(".")[0].isupper() else h
+            for w in WANT:
+                if h == w or h.endswith("." + w) or key == w:
+                    d[w] = f"{v} {u}".strip()
+        out.append((kn, d))
+    return out
+
+
+def text(name):
+    path = os.path.join(P, name)
+    return open(path).read().rstrip() if os.path.exists(path) else None
+
+
+def main():
+    o = sys.stdout
+    o.write("# Round 2 profile summary (B200, sm_100a)\n\n")
+    o.write("Everything below is copied from files in this directory; regenerate with `python tools/make_profile_summary.py`. "
+            "ncu ran with `--clock-control none`; numbers printed under ncu are never bench values.\n\n")
+    o.write("## Bench lines (`bench.py`, CUDA-event timing, max over ranks)\n\n")
+    o.write("| file | workload | N | value (resident) | e2e f32 | e2e i16 | ms/step | roofline K2s | cpu_baseline |\n|---|---|---|---|---|---|---|---|---|\n")
+    for f in sorted(os.listdir(P)):
+        if not (f.startswith("r02_bench") and f.endswith(".json")):
+            continue
+        j = load_json_line(f)
+        if not j or "value" not in j:
+            continue
+        rf = j.get("roofline") or {}
+        cb = j.get("cpu_baseline") or {}
+        wl = (j.get("config") or {}).get("workload", "")[:60]
+        e16 = (j.get("e2e_i16") or {}).get("value")
+        o.write(f"| `{f}` | {wl}… | {j.get('n_gpus')} | {j['value'] / 1e6:.1f} M | {(j.get('e2e') or {}).get('value', 0) / 1e6:.1f} M | "
+                f"{(e16 or 0) / 1e6:.1f} M | {j.get('ms_per_step')} | {rf.get('achieved', '')} / {rf.get('peak', '')} {rf.get('unit', '')} = {rf.get('frac', '')} | "
+                f"{cb.get('value', '')} {cb.get('unit', '')} ({cb.get('cores', '')} threads) |\n")
+    o.write("\n")
+    for f in sorted(os.listdir(P)):
+        if f.startswith("r02_bench") and f.endswith(".json"):
+            j = load_json_line(f)
+            if j and "impl" in j:
+                o.write(f"Reference arm (`{f}`): {j.get('value')} {j.get('unit')} with {(j.get('cpu_baseline') or {}).get('cores')} host threads.\n\n")
+    for key in ("mfcc_microbench", "cadence"):
+        j = load_json_line("r02_bench_config5_n1.json") or {}
+        if key in j:
+            o.write(f"`{key}` (same line): `{json.dumps(j[key])[:900]}`\n\n")
+
+    ls = launch_shares("r02_launches.csv")
+    if ls:
+        tot, cnt = ls
+        T = sum(tot.values())
+        o.write("## Launch list shares (`r02_launches.csv`: `ncu --metrics gpu__time_duration.sum` over a short bench command; cold-cache, serialised)\n\n")
+        o.write("| kernel | launches | total ms | share |\n|---|---|---|---|\n")
+        for k, v in tot.most_common(12):
+            o.write(f"| `{k}` | {cnt[k]} | {v:.3f} | {100 * v / T:.1f}% |\n")
+        ours = {k: v for k, v in tot.items() if not k.startswith("torch")}
+        To = sum(ours.values())
+        o.write("\nShares of our kernels only: " + ", ".join(f"`{k.split('<')[0]}` {100 * v / To:.1f} %" for k, v in sorted(ours.items(), key=lambda kv: -kv[1])[:6]) + ".\n\n")
+
+    o.write("## Full captures (`ncu --set full`, raw pages `r02_ncu_*_raw.csv`)\n\n")
+    for f in sorted(os.listdir(P)):
+        if f.startswith("r02_ncu_") and f.endswith("_raw.csv"):
+            for kn, d in raw_page(f) or []:
+                o.write(f"### `{f}` — `{kn[:110]}`\n\n| metric | value |\n|---|---|\n")
+                for w in WANT:
+                    if w in d:
+                        o.write(f"| {w} | {d[w]} |\n")
+                o.write("\n")
+
+    for title, f in (("K2s ceiling micro-benchmark (`tools/microbench_k2s_ceiling.cu`)", "r02_k2s_ceiling2.txt"),
+                     ("K2s phase accounting of the shipped kernel (`tools/profile_k2s_phases.cu`) and the role-rotation experiment", "r02_k2s_phases.txt"),
+                     ("K2s v5 experiment (bulk-copy loaders), A/B", "r02_ab_stream5.txt"),
+                     ("K1 observed error vs the oracle", "r02_k1_error.json"),
+                     ("compute-sanitizer memcheck, whole `-m gpu` suite", "r02_sanitizer_memcheck.txt"),
+                     ("compute-sanitizer racecheck, window-kernel tests (K2p, K2c)", "r02_sanitizer_racecheck_window_kernels.txt"),
+                     ("compute-sanitizer racecheck, K1 / K2s / generic DTW / filter tests", "r02_sanitizer_racecheck_kernels.txt"),
+                     ("`pytest -m gpu` on the B200", "r02_pytest_gpu.txt")):
+        t = text(f)
+        if t:
+            t = "\n".join(t.splitlines()[-60:])
+            o.write(f"## {title} — `{f}`\n\n```\n{t}\n```\n\n")
+    o.write("SASS evidence (FFMA2 / FMNMX3 / UBLKCP / SYNCS / USETMAXREG / LDCU per kernel; no HMMA / UTCMMA / LDTM): `r02_sass_summary.md`.\n")
+
+
+if __name__ == "__main__":
+    main()
