@@ -8,8 +8,12 @@
 #include <cstdlib>
 #include <vector>
 
+#ifndef K2S_SRC
 #define RP_K2S_PROFILE 1
 #include "../rustpotter_b200/csrc/dtw_stream4_kernel.cu"
+#else   // plain timing of another copy of the kernel source (same-box A/B of source variants)
+#include K2S_SRC
+#endif
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e_)); return 1; } } while (0)
 
@@ -33,15 +37,21 @@ int main(int argc, char** argv) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
-    for (int rep = 0; rep < 3; rep++) {
+    for (int rep = 0; rep < (argc > 2 ? atoi(argv[2]) : 3); rep++) {
+#ifdef RP_K2S_PROFILE
         unsigned long long zero[8][8] = {};
         CK(cudaMemcpyToSymbol(rp::g_prof, zero, sizeof(zero)));
+#endif
         CK(cudaEventRecord(e0));
         CK(rp::launch_dtw_pairs_stream4(a, 0));
         CK(cudaEventRecord(e1));
         CK(cudaDeviceSynchronize());
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, e0, e1));
+#ifndef RP_K2S_PROFILE
+        printf("%.4f ms\n", ms);
+        continue;
+#else
         unsigned long long h[8][8];
         CK(cudaMemcpyFromSymbol(h, rp::g_prof, sizeof(h)));
         if (rep < 2) continue;
@@ -60,6 +70,7 @@ int main(int argc, char** argv) {
         }
         printf("producer warps, cycles per group: waiting for free slots / loads + scale + store\n");
         for (int w = 4; w < 8; w++) printf("  %d   %8.0f   %8.0f\n", w, h[w][1] / groups, h[w][2] / groups);
+#endif
     }
     return 0;
 }
