@@ -116,6 +116,31 @@ __device__ __forceinline__ Row16 ldc_row(int f4_index) {
     return r;
 }
 
+// Shared memory through 32-bit shared-space addresses (the row loop keeps two of them in registers; built from generic
+// pointers the compiler re-derived the CTA's shared window base -- S2UR, ULEA, LEA -- at every use: 6 % of the loop).
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float lds32(unsigned a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ Row16 lds_row_sa(unsigned a) {
+    Row16 r;
+#pragma unroll
+    for (int q = 0; q < 4; q++) asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(r.p[2 * q]), "=l"(r.p[2 * q + 1]) : "r"(a + 16 * q));
+    return r;
+}
+// all warps of the CTA, from whichever of the role loops they run (every warp is in one role as a whole)
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
+// 1/sqrt(n2) for the squared norm of a column; 0 for a zero vector (similarity 0, comparator.rs:44-47). MUFU.RSQ without the
+// denormal rescue code of rsqrtf (four instructions per row): a squared norm is 0 or far above FLT_MIN.
+__device__ __forceinline__ float inv_norm(float n2) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(n2));
+    return n2 >= FLT_MIN ? y : 0.f;
+}
+
 struct WindowLaunch {              // what one launch covers (device pointers)
     const int32_t* slots;          // [n_slots] slot ids of this launch, or nullptr: slot i = i
     int n_slots;
@@ -254,27 +279,30 @@ dtw_windows_d16_kernel(DtwWindowsArgs a, WindowLaunch L, const float* __restrict
             const f2 y = add2(x.p[q], nmu[q]);
             nn = fma2(y, y, nn);
         }
-        const float n2 = hsum(nn);
-        return n2 > 0.f ? rsqrtf(n2) : 0.f;
+        return inv_norm(hsum(nn));
     };
     if (dp) {
 #pragma unroll
         for (int c = 1; c < W; c++) inv[c % NB] = col_inv(t + c - 1);
     }
 
+    // ---- the rows. Three loops, one per role of a warp (DP windows / helper / tail warp without a live window), each with one
+    // CTA barrier per row: no divergence bookkeeping inside the loop.
     const int last_row = m - 1;  // rows 1 .. m-1 (the result lives in row m-1)
-    for (int r0 = 0; r0 < last_row; r0 += NB) {
+    if (dp) {
+        unsigned g_sa = smem_u32(Gs) + 4u * (unsigned)t;                              // &G[0][t]
+        unsigned x_sa = smem_u32(Xs) + (unsigned)(kXS * 4) * (unsigned)(t + W - 1);   // frame u = t + r + W - 2 of row r = 1
+        asm volatile("" : "+r"(g_sa), "+r"(x_sa));
+        for (int r0 = 0; r0 < last_row; r0 += NB) {
 #pragma unroll
-        for (int k = 0; k < NB; k++) {
-            const int r = r0 + k + 1;  // r % NB == (k + 1) % NB because r0 is a multiple of NB
-            if (r <= last_row) {       // uniform over the CTA
-                float* G = Gs + (r & 1) * GS;
-                const Row16 ar = CT ? ldc_row(c_row0 + (r - 1) * 4) : lds_row(Ts + (r - 1) * kD);  // the same for the whole CTA
-                float A = 0.f;
-                if (dp) {
+            for (int k = 0; k < NB; k++) {
+                const int r = r0 + k + 1;  // r % NB == (k + 1) % NB because r0 is a multiple of NB (and NB is even: r & 1 == (k + 1) & 1)
+                if (r <= last_row) {       // uniform over the CTA
+                    const unsigned g_row = g_sa + (unsigned)(((k + 1) & 1) * GS * 4);
+                    const Row16 ar = CT ? ldc_row(c_row0 + (r - 1) * 4) : lds_row(Ts + (r - 1) * kD);  // the same for the whole CTA
                     // own new column c = r+W-1 <-> frame u = t + r + W - 2
-                    const int u = t + r + W - 2;
-                    const Row16 x = lds_row(Xs + u * kXS);
+                    const Row16 x = lds_row_sa(x_sa);
+                    x_sa += kXS * 4;
                     f2 nn = 0ull, g = 0ull, aa = 0ull;
 #pragma unroll
                     for (int q = 0; q < 8; q++) {
@@ -283,33 +311,15 @@ dtw_windows_d16_kernel(DtwWindowsArgs a, WindowLaunch L, const float* __restrict
                         g = fma2(ar.p[q], x.p[q], g);
                         aa = fma2(ar.p[q], nmu[q], aa);
                     }
-                    const float n2 = hsum(nn);
-                    inv[(k + W) % NB] = n2 > 0.f ? rsqrtf(n2) : 0.f;  // column r+W-1 = (k+1)+W-1 mod NB
-                    G[t + NB - 1] = hsum(g);
-                    A = -hsum(aa);                                     // a^_r . mu  (nmu is negated)
-                } else if (tid >= kNW) {
-                    // helper warp: the NB-1 lowest frames of this row's shared range (a second pass only when NB-1 > 32)
-                    const int e0 = tid - kNW;
-                    if (e0 < NB - 1) {
-                        const int u = r - W - 1 + e0;
-                        float g = 0.f;
-                        if (u >= 0) g = dot16(ar, lds_row(Xs + u * kXS));
-                        G[e0] = g;
-                    }
-                    if (NB - 1 > 32 && e0 + 32 < NB - 1) {
-                        const int u = r - W - 1 + e0 + 32;
-                        float g = 0.f;
-                        if (u >= 0) g = dot16(ar, lds_row(Xs + u * kXS));
-                        G[e0 + 32] = g;
-                    }
-                }
-                __syncthreads();
-                if (dp) {
+                    inv[(k + W) % NB] = inv_norm(hsum(nn));  // column r+W-1 = (k+1)+W-1 mod NB
+                    sts32(g_row + (NB - 1) * 4, hsum(g));
+                    const float A = -hsum(aa);                // a^_r . mu  (nmu is negated)
+                    cta_sync();
                     if (r == 1) {
                         // row 1: columns c < 1 must stay +inf (they would otherwise inherit D[0][0])
 #pragma unroll
                         for (int i = W; i < NB; i++) {
-                            const float sim = (G[t + i] - A) * inv[(k + i + 1 + NB - W) % NB];
+                            const float sim = (lds32(g_row + i * 4) - A) * inv[(k + i + 1 + NB - W) % NB];
                             const float best = min3(i + 1 < NB ? D[i + 1] : INFINITY, D[i], D[i - 1]);
                             const float v = (1.f - sim) + best;
                             D[i] = (!MASK || ((band_mask >> i) & 1ull)) ? v : INFINITY;
@@ -319,7 +329,7 @@ dtw_windows_d16_kernel(DtwWindowsArgs a, WindowLaunch L, const float* __restrict
 #pragma unroll
                         for (int i = 0; i < NB; i++) {
                             // column c = r - W + i  ->  inv slot c % NB = (k + 1 - W + i) mod NB
-                            const float sim = (G[t + i] - A) * inv[(k + i + 1 + NB - W) % NB];
+                            const float sim = (lds32(g_row + i * 4) - A) * inv[(k + i + 1 + NB - W) % NB];
                             const float best = min3(i + 1 < NB ? D[i + 1] : INFINITY, D[i], i > 0 ? D[i - 1] : INFINITY);
                             const float v = (1.f - sim) + best;
                             D[i] = (!MASK || ((band_mask >> i) & 1ull)) ? v : INFINITY;
@@ -328,6 +338,28 @@ dtw_windows_d16_kernel(DtwWindowsArgs a, WindowLaunch L, const float* __restrict
                 }
             }
         }
+    } else if (tid >= kNW) {
+        // helper warp: the NB-1 lowest frames of each row's shared range (a second pass only when NB-1 > 32)
+        const int e0 = tid - kNW;
+        for (int r = 1; r <= last_row; r++) {
+            float* G = Gs + (r & 1) * GS;
+            const Row16 ar = CT ? ldc_row(c_row0 + (r - 1) * 4) : lds_row(Ts + (r - 1) * kD);
+            if (e0 < NB - 1) {
+                const int u = r - W - 1 + e0;
+                float g = 0.f;
+                if (u >= 0) g = dot16(ar, lds_row(Xs + u * kXS));
+                G[e0] = g;
+            }
+            if (NB - 1 > 32 && e0 + 32 < NB - 1) {
+                const int u = r - W - 1 + e0 + 32;
+                float g = 0.f;
+                if (u >= 0) g = dot16(ar, lds_row(Xs + u * kXS));
+                G[e0 + 32] = g;
+            }
+            cta_sync();
+        }
+    } else {
+        for (int r = 1; r <= last_row; r++) cta_sync();
     }
     bool pass = false;
     if (live) {
