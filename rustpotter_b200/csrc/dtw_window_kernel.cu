@@ -161,8 +161,8 @@ dtw_windows_d16_kernel(DtwWindowsArgs a, WindowLaunch L, const float* __restrict
     extern __shared__ __align__(16) float sm[];
     // The arrays the row loop touches sit at compile-time offsets (no address arithmetic on runtime sizes in the loop).
     constexpr int GS = kNW + NB;
-    float* Gs = sm;                              // [2][kNW + NB] shared dot products, double buffered
-    float* Os = Gs + 2 * GS;                     // [kThreads/16 + 1][16] segment offsets of the row prefix (16 B aligned)
+    float* Gs = sm;                              // [2][2][kNW + NB] shared dot products: two rows per barrier, double buffered
+    float* Os = Gs + 4 * GS;                     // [kThreads/16 + 1][16] segment offsets of the row prefix (16 B aligned)
     float* Xs = Os + (kThreads / 16 + 1) * kD;   // [x_rows][kXS] frame tile (raw frames)
     float* Ts = Xs + (size_t)x_rows * kXS;       // [max_len][16] unit template rows
     const int p_rows = kNW + a.max_len + 1;      // prefix rows 0 .. kNW + m
@@ -289,77 +289,88 @@ dtw_windows_d16_kernel(DtwWindowsArgs a, WindowLaunch L, const float* __restrict
     // ---- the rows. Three loops, one per role of a warp (DP windows / helper / tail warp without a live window), each with one
     // CTA barrier per row: no divergence bookkeeping inside the loop.
     const int last_row = m - 1;  // rows 1 .. m-1 (the result lives in row m-1)
+    // Two rows per barrier: [column work of rows r, r+1] barrier [DP of rows r, r+1]; pair p = (r-1)/2 uses G buffers 2(p&1), 2(p&1)+1.
     if (dp) {
         unsigned g_sa = smem_u32(Gs) + 4u * (unsigned)t;                              // &G[0][t]
         unsigned x_sa = smem_u32(Xs) + (unsigned)(kXS * 4) * (unsigned)(t + W - 1);   // frame u = t + r + W - 2 of row r = 1
         asm volatile("" : "+r"(g_sa), "+r"(x_sa));
+        // column work of row r (band slot k): own new column c = r+W-1 <-> frame u = t + r + W - 2; returns A = a^_r . mu
+        auto column = [&](int r, int k, unsigned g_row) -> float {
+            const Row16 ar = CT ? ldc_row(c_row0 + (r - 1) * 4) : lds_row(Ts + (r - 1) * kD);  // the same for the whole CTA
+            const Row16 x = lds_row_sa(x_sa);
+            x_sa += kXS * 4;
+            f2 nn = 0ull, g = 0ull, aa = 0ull;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const f2 y = add2(x.p[q], nmu[q]);
+                nn = fma2(y, y, nn);
+                g = fma2(ar.p[q], x.p[q], g);
+                aa = fma2(ar.p[q], nmu[q], aa);
+            }
+            inv[(k + W) % NB] = inv_norm(hsum(nn));  // column r+W-1 = (k+1)+W-1 mod NB
+            sts32(g_row + (NB - 1) * 4, hsum(g));
+            return -hsum(aa);                         // (nmu is negated)
+        };
+        // inv0: 1/|x - mu| of the row's leftmost band column r-W (its ring slot is the one column r+W takes over)
+        auto dp_row = [&](int k, unsigned g_row, float A, bool first, float inv0) {
+            if (first) {
+                // row 1: columns c < 1 must stay +inf (they would otherwise inherit D[0][0])
+#pragma unroll
+                for (int i = W; i < NB; i++) {
+                    const float sim = (lds32(g_row + i * 4) - A) * inv[(k + i + 1 + NB - W) % NB];
+                    const float best = min3(i + 1 < NB ? D[i + 1] : INFINITY, D[i], D[i - 1]);
+                    const float v = (1.f - sim) + best;
+                    D[i] = (!MASK || ((band_mask >> i) & 1ull)) ? v : INFINITY;
+                }
+                D[W - 1] = INFINITY;
+            } else {
+#pragma unroll
+                for (int i = 0; i < NB; i++) {
+                    // column c = r - W + i  ->  inv slot c % NB = (k + 1 - W + i) mod NB
+                    const float sim = (lds32(g_row + i * 4) - A) * (i == 0 ? inv0 : inv[(k + i + 1 + NB - W) % NB]);
+                    const float best = min3(i + 1 < NB ? D[i + 1] : INFINITY, D[i], i > 0 ? D[i - 1] : INFINITY);
+                    const float v = (1.f - sim) + best;
+                    D[i] = (!MASK || ((band_mask >> i) & 1ull)) ? v : INFINITY;
+                }
+            }
+        };
+        unsigned g_pair = 0;   // byte offset of the pair's two G buffers: alternates 0, 2 GS floats
         for (int r0 = 0; r0 < last_row; r0 += NB) {
 #pragma unroll
-            for (int k = 0; k < NB; k++) {
-                const int r = r0 + k + 1;  // r % NB == (k + 1) % NB because r0 is a multiple of NB (and NB is even: r & 1 == (k + 1) & 1)
+            for (int k = 0; k < NB; k += 2) {
+                const int r = r0 + k + 1;  // r % NB == (k + 1) % NB because r0 is a multiple of NB
                 if (r <= last_row) {       // uniform over the CTA
-                    const unsigned g_row = g_sa + (unsigned)(((k + 1) & 1) * GS * 4);
-                    const Row16 ar = CT ? ldc_row(c_row0 + (r - 1) * 4) : lds_row(Ts + (r - 1) * kD);  // the same for the whole CTA
-                    // own new column c = r+W-1 <-> frame u = t + r + W - 2
-                    const Row16 x = lds_row_sa(x_sa);
-                    x_sa += kXS * 4;
-                    f2 nn = 0ull, g = 0ull, aa = 0ull;
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        const f2 y = add2(x.p[q], nmu[q]);
-                        nn = fma2(y, y, nn);
-                        g = fma2(ar.p[q], x.p[q], g);
-                        aa = fma2(ar.p[q], nmu[q], aa);
-                    }
-                    inv[(k + W) % NB] = inv_norm(hsum(nn));  // column r+W-1 = (k+1)+W-1 mod NB
-                    sts32(g_row + (NB - 1) * 4, hsum(g));
-                    const float A = -hsum(aa);                // a^_r . mu  (nmu is negated)
+                    const unsigned g_a = g_sa + g_pair, g_b = g_a + (unsigned)(GS * 4);
+                    g_pair ^= (unsigned)(2 * GS * 4);
+                    const bool two = r + 1 <= last_row;
+                    const float A = column(r, k, g_a);
+                    const float inv_left = inv[(k + 1 + W) % NB];   // column r-W, before column r+1+W-1 = r+W takes its slot
+                    float A2 = 0.f;
+                    if (two) A2 = column(r + 1, k + 1, g_b);
                     cta_sync();
-                    if (r == 1) {
-                        // row 1: columns c < 1 must stay +inf (they would otherwise inherit D[0][0])
-#pragma unroll
-                        for (int i = W; i < NB; i++) {
-                            const float sim = (lds32(g_row + i * 4) - A) * inv[(k + i + 1 + NB - W) % NB];
-                            const float best = min3(i + 1 < NB ? D[i + 1] : INFINITY, D[i], D[i - 1]);
-                            const float v = (1.f - sim) + best;
-                            D[i] = (!MASK || ((band_mask >> i) & 1ull)) ? v : INFINITY;
-                        }
-                        D[W - 1] = INFINITY;
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < NB; i++) {
-                            // column c = r - W + i  ->  inv slot c % NB = (k + 1 - W + i) mod NB
-                            const float sim = (lds32(g_row + i * 4) - A) * inv[(k + i + 1 + NB - W) % NB];
-                            const float best = min3(i + 1 < NB ? D[i + 1] : INFINITY, D[i], i > 0 ? D[i - 1] : INFINITY);
-                            const float v = (1.f - sim) + best;
-                            D[i] = (!MASK || ((band_mask >> i) & 1ull)) ? v : INFINITY;
-                        }
-                    }
+                    dp_row(k, g_a, A, r == 1, inv_left);
+                    if (two) dp_row(k + 1, g_b, A2, false, inv[(k + 2 + W) % NB]);
                 }
             }
         }
     } else if (tid >= kNW) {
-        // helper warp: the NB-1 lowest frames of each row's shared range (a second pass only when NB-1 > 32)
+        // helper warp: the NB-1 lowest frames of each row's shared range, both rows of a pair
         const int e0 = tid - kNW;
-        for (int r = 1; r <= last_row; r++) {
-            float* G = Gs + (r & 1) * GS;
-            const Row16 ar = CT ? ldc_row(c_row0 + (r - 1) * 4) : lds_row(Ts + (r - 1) * kD);
-            if (e0 < NB - 1) {
-                const int u = r - W - 1 + e0;
+        for (int r = 1; r <= last_row; r += 2) {
+            const int rows = r + 1 <= last_row ? 2 : 1;
+            float* G = Gs + ((((r - 1) >> 1) & 1) * 2) * GS;
+            for (int idx = e0; idx < rows * (NB - 1); idx += 32) {
+                const int rr = idx >= NB - 1 ? 1 : 0, e = idx - rr * (NB - 1);
+                const Row16 ar = CT ? ldc_row(c_row0 + (r + rr - 1) * 4) : lds_row(Ts + (r + rr - 1) * kD);
+                const int u = r + rr - W - 1 + e;
                 float g = 0.f;
                 if (u >= 0) g = dot16(ar, lds_row(Xs + u * kXS));
-                G[e0] = g;
-            }
-            if (NB - 1 > 32 && e0 + 32 < NB - 1) {
-                const int u = r - W - 1 + e0 + 32;
-                float g = 0.f;
-                if (u >= 0) g = dot16(ar, lds_row(Xs + u * kXS));
-                G[e0 + 32] = g;
+                G[rr * GS + e] = g;
             }
             cta_sync();
         }
     } else {
-        for (int r = 1; r <= last_row; r++) cta_sync();
+        for (int r = 1; r <= last_row; r += 2) cta_sync();
     }
     bool pass = false;
     if (live) {
@@ -450,7 +461,7 @@ cudaError_t launch_instance(const DtwWindowsArgs& a, WindowLaunch L, const float
     if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
     const int x_rows = kNW + a.max_len + W + 1;
     const int p_rows = kNW + a.max_len + 1;
-    const size_t bytes = ((size_t)x_rows * kXS + (size_t)a.max_len * kD + 2 * (kNW + 2 * W) + (kThreads / 16 + 1) * kD +
+    const size_t bytes = ((size_t)x_rows * kXS + (size_t)a.max_len * kD + 4 * (kNW + 2 * W) + (kThreads / 16 + 1) * kD +
                           (size_t)p_rows * kD) * sizeof(float);
     if (bytes > 200 * 1024) return cudaErrorInvalidValue;
     int dev = 0;
