@@ -131,8 +131,10 @@ __device__ __forceinline__ Row16 lds_row_sa(unsigned a) {
     for (int q = 0; q < 4; q++) asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(r.p[2 * q]), "=l"(r.p[2 * q + 1]) : "r"(a + 16 * q));
     return r;
 }
-// all warps of the CTA, from whichever of the role loops they run (every warp is in one role as a whole)
-__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
+// All warps of the CTA, from whichever of the role loops they run (every warp is in one role as a whole). A counted named
+// barrier in its non-aligned form: the three loops reach it from different program locations, which neither __syncthreads()
+// nor an aligned bar.sync allow (compute-sanitizer synccheck reports the aligned form as divergence; this form is clean).
+__device__ __forceinline__ void cta_sync() { asm volatile("barrier.sync 1, %0;" ::"n"(kThreads) : "memory"); }
 // 1/sqrt(n2) for the squared norm of a column; 0 for a zero vector (similarity 0, comparator.rs:44-47). MUFU.RSQ without the
 // denormal rescue code of rsqrtf (four instructions per row): a squared norm is 0 or far above FLT_MIN.
 __device__ __forceinline__ float inv_norm(float n2) {
@@ -359,13 +361,14 @@ dtw_windows_d16_kernel(DtwWindowsArgs a, WindowLaunch L, const float* __restrict
         for (int r = 1; r <= last_row; r += 2) {
             const int rows = r + 1 <= last_row ? 2 : 1;
             float* G = Gs + ((((r - 1) >> 1) & 1) * 2) * GS;
-            for (int idx = e0; idx < rows * (NB - 1); idx += 32) {
-                const int rr = idx >= NB - 1 ? 1 : 0, e = idx - rr * (NB - 1);
+            for (int base = 0; base < rows * (NB - 1); base += 32) {   // uniform trip count; no lane leaves the warp's path
+                const int idx = base + e0;
+                const bool act = idx < rows * (NB - 1);
+                const int rr = (act && idx >= NB - 1) ? 1 : 0, e = act ? idx - rr * (NB - 1) : 0;
                 const Row16 ar = CT ? ldc_row(c_row0 + (r + rr - 1) * 4) : lds_row(Ts + (r + rr - 1) * kD);
                 const int u = r + rr - W - 1 + e;
-                float g = 0.f;
-                if (u >= 0) g = dot16(ar, lds_row(Xs + u * kXS));
-                G[rr * GS + e] = g;
+                const float g = dot16(ar, lds_row(Xs + max(u, 0) * kXS));
+                if (act) G[rr * GS + e] = u >= 0 ? g : 0.f;
             }
             cta_sync();
         }
