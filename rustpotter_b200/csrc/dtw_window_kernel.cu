@@ -215,7 +215,10 @@ dtw_windows_d16_kernel(DtwWindowsArgs a, WindowLaunch L, const float* __restrict
     // DP thread (one window) vs helper warp; a DP warp whose 32 windows all lie beyond n_new (tail block) only
     // keeps the barriers company: nothing it would produce is read by a live window (G_r[u] of thread t is
     // consumed by threads t..t+2W-1 only)
-    const bool dp = tid < kNW && (j0 + (tid & ~31)) < a.n_new;
+    // (the warp index through a lane-0 broadcast: the compiler then knows the role branches are warp-uniform and keeps the
+    // template row, the loop counters and the addresses on the uniform datapath inside them)
+    const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const bool dp = warp_u < kNW / 32 && (j0 + warp_u * 32) < a.n_new;
     const int t = dp ? tid : 0;
     const bool live = dp && (j0 + tid) < a.n_new;
 
@@ -355,7 +358,7 @@ dtw_windows_d16_kernel(DtwWindowsArgs a, WindowLaunch L, const float* __restrict
                 }
             }
         }
-    } else if (tid >= kNW) {
+    } else if (warp_u >= kNW / 32) {
         // helper warp: the NB-1 lowest frames of each row's shared range, both rows of a pair
         const int e0 = tid - kNW;
         for (int r = 1; r <= last_row; r += 2) {
