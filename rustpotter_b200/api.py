@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librustpotter_b200.so")
+# RP_LIB_PATH: another build of the same library (same-box A/B measurements of kernel variants; debug only)
+LIB_PATH = os.environ.get("RP_LIB_PATH") or os.path.join(_HERE, "librustpotter_b200.so")
 NAME_MAX = 128
 
 SCORE_MODES = {"average": 0, "max": 1, "median": 2, "p25": 3, "p50": 4, "p75": 5, "p80": 6, "p90": 7, "p95": 8}

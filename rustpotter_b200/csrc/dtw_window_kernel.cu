@@ -157,6 +157,8 @@ struct WindowLaunch {              // what one launch covers (device pointers)
 };
 
 template <int W, bool CT, bool MASK>
+// (4 or 6 CTAs per SM for W = 5 -- 91 registers without spills, 64 with 32 bytes of them -- measured within +-1.5 % of 5;
+// rotating the helper role over the five warps by CTA measured 8 % slower)
 __global__ void __launch_bounds__(kThreads, (W <= 5 ? 5 : W <= 8 ? 3 : 2))
 dtw_windows_d16_kernel(DtwWindowsArgs a, WindowLaunch L, const float* __restrict__ tmpl_unit, int x_rows, int j_blocks) {
     constexpr int NB = 2 * W;  // band cells per row
