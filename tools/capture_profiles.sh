@@ -16,6 +16,6 @@ cap() {  # name, kernel regex, launches to skip, command...
 }
 cap k2p dtw_windows_d16 3 python tools/prof_pipeline.py 2048 5 1
 cap k1 mfcc_frames2 2 python tools/prof_pipeline.py 2048 5 1
-cap k2c dtw_windows_cadence 110 python tools/prof_cadence.py 4096 5 125
+cap k2c dtw_windows_cadence 40 python tools/prof_cadence.py 4096 5 125
 cap k2s dtw_pairs_stream4 1 python tools/prof_dtw_stream.py 1000000
 ls -la $O | tail -20

@@ -97,7 +97,7 @@ def main():
         if not (f.startswith("r02_bench") and f.endswith(".json")):
             continue
         j = load_json_line(f)
-        if not j or "value" not in j:
+        if not j or "value" not in j or "impl" in j:
             continue
         rf = j.get("roofline") or {}
         cb = j.get("cpu_baseline") or {}
@@ -146,6 +146,7 @@ def main():
                      ("compute-sanitizer memcheck, whole `-m gpu` suite", "r02_sanitizer_memcheck.txt"),
                      ("compute-sanitizer racecheck, window-kernel tests (K2p, K2c)", "r02_sanitizer_racecheck_window_kernels.txt"),
                      ("compute-sanitizer racecheck, K1 / K2s / generic DTW / filter tests", "r02_sanitizer_racecheck_kernels.txt"),
+                     ("compute-sanitizer synccheck, whole `-m gpu` suite", "r02_sanitizer_synccheck.txt"),
                      ("`pytest -m gpu` on the B200", "r02_pytest_gpu.txt")):
         t = text(f)
         if t:
