@@ -428,3 +428,28 @@ def test_resampler_matches_oracle_and_a_float64_reference(rate):
     # a 440 Hz tone survives with its amplitude (unit passband gain)
     mid = ref[nout:-nout]
     assert 0.3 < np.abs(mid).max() < 0.8
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) works without a GPU and prints ONE JSON line with
+    our arm's metric string, unit and config plus the keys the contract names."""
+    import json
+    import subprocess
+    import sys
+
+    import bench
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["metric"] == bench.METRIC and j["unit"] == "windows/s"
+    assert j["higher_is_better"] is True and j["n_gpus"] == 1 and j["steps"] == 1 and j["warmup"] == 1
+    assert j["value"] > 0 and j["ms_per_step"] > 0
+    assert j["e2e"] == {"value": j["value"], "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = j["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == j["value"] and "sample" in cb
+    assert "configs[4]" in j["config"]["workload"]
