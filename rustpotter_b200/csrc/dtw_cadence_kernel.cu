@@ -9,10 +9,10 @@
 // Here a HALF-WARP scores up to three consecutive windows of one stream against one template, the two halves of a warp
 // two streams against the same template (so the template row is fetched once for both):
 //   lanes 0 .. 2W+1 of the half   one frame each of the row's shared range: G_r[u] (a 16-dim dot, 8 FFMA2)
-//   lanes 12 .. 14                A_r of window 0 .. 2  (the same dot against the window's mean)
+//   lanes 12 .. 14                A_r of window 0 .. 2  (the same dot against the window's mean, which they keep in registers)
 //   lanes 0 .. 2 again            the thread-serial in-place band DP of window 0 .. 2 (K2p's; G and A arrive by shuffle)
 // A CTA = all templates ("slots") of a stream pair's window triple, one warp each (each stream's ~105 frames are staged
-// in shared memory once); the template row, identical for the warp, is read from L2 one row ahead. ~80 warp instructions
+// in shared memory once); the template row, identical for the warp, is a broadcast load from L1 / L2. ~80 warp instructions
 // per template row for six windows: well below K2p's efficiency on long calls, several times faster on short ones
 // (4096 streams x 36 templates, 30 ms calls: see DESIGN.md section 6). The engine takes this kernel when a call brings at
 // most 24 new windows per stream.
@@ -78,15 +78,23 @@ __device__ __forceinline__ float dot16(const Row16& a, const Row16& b) {
     return hsum(acc);
 }
 
+// Floats per stream tile: the second stream's tile starts 16 banks after the first's, so the two halves of a warp reading the
+// same (row, coefficient) of their streams (the window means) do not meet in a bank.
+__host__ __device__ inline int x_tile_floats(int x_rows) {
+    const int n = x_rows * kXS;
+    return n + ((16 - n % 32) + 32) % 32;
+}
+
 // grid: ceil(n_streams / 2) * triples CTAs; block: n_warps * 32 threads; dynamic shared memory:
 //   Xs[2][x_rows][kXS] frames of the two streams | per warp and half: Mu[NWIN][16] (negated means) | Inv[NWIN][inv_cols]
-__global__ void __launch_bounds__(kMaxWarps * 32) dtw_windows_cadence_kernel(DtwWindowsArgs a, const float* __restrict__ tmpl_unit,
+__global__ void __launch_bounds__(kMaxWarps * 32, 2) dtw_windows_cadence_kernel(DtwWindowsArgs a, const float* __restrict__ tmpl_unit,
                                                                             const int64_t* __restrict__ unit_off, int triples, int x_rows,
                                                                             int inv_cols) {
     extern __shared__ __align__(16) float sm[];
     const int n_warps = blockDim.x >> 5;
     float* XsAll = sm;
-    float* MuAll = XsAll + (size_t)2 * x_rows * kXS;
+    const int x_tile = x_tile_floats(x_rows);
+    float* MuAll = XsAll + (size_t)2 * x_tile;
     float* InvAll = MuAll + (size_t)n_warps * 2 * NWIN * kD;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int half = lane >> 4, hl = lane & 15, hbase = lane & 16;   // half-warp, lane inside it, its first lane
@@ -98,7 +106,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) dtw_windows_cadence_kernel(Dtw
     // ---- stage the frames of the triple for both streams: window jj covers tile rows jj .. jj + m - 1
     for (int h = 0; h < 2; h++) {
         const int64_t b = 2 * pair + h;
-        float* Xh = XsAll + (size_t)h * x_rows * kXS;
+        float* Xh = XsAll + (size_t)h * x_tile;
         const int64_t row0 = (int64_t)a.first_window_row + j0;
         const int64_t avail = b < a.n_streams ? a.frame_rows - row0 : 0;   // (an odd stream count: the last pair's second half is zeros)
         if (a.d == kD) {
@@ -120,7 +128,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) dtw_windows_cadence_kernel(Dtw
     __syncthreads();
 
     const int64_t b = 2 * pair + half;                          // this half-warp's stream
-    const float* Xs = XsAll + (size_t)half * x_rows * kXS;
+    const float* Xs = XsAll + (size_t)half * x_tile;
     float* Mu = MuAll + (size_t)(warp * 2 + half) * (NWIN * kD);
     float* Inv = InvAll + (size_t)(warp * 2 + half) * NWIN * inv_cols;
     const unsigned band_mask = ((1u << (2 * a.band)) - 1u) << (W - a.band);   // cells inside [r-band, r+band-1]
@@ -174,19 +182,21 @@ __global__ void __launch_bounds__(kMaxWarps * 32) dtw_windows_cadence_kernel(Dtw
         for (int c = 1; c < W; c++) inv[c % NB] = Invw[c];       // columns 1 .. W-1 enter the band before row 1
 
         const int last_row = m - 1;
-        Row16 ar_next = ld_row(trow);                            // row 1 (index 0)
+        Row16 v = ld_row(is_a ? Mu + (hl - 12) * kD : Xs);       // A lanes: the window's negated mean, for every row
         for (int r0 = 0; r0 < last_row; r0 += NB) {
 #pragma unroll
             for (int k = 0; k < NB; k++) {
                 const int r = r0 + k + 1;
                 if (r <= last_row) {                             // warp-uniform
-                    const Row16 ar = ar_next;
-                    if (r < last_row) ar_next = ld_row(trow + (size_t)r * kD);   // one row ahead (L2)
+                    // the template row, the same for the whole warp: an L1 / L2 broadcast load. (Fetching it one row ahead
+                    // costs 16 registers: with the A lanes' means resident that spills at two CTAs per SM -- measured 2.12 ms
+                    // per call against 1.53 without the look-ahead and 1.78 for the round's first version.)
+                    const Row16 ar = ld_row(trow + (size_t)(r - 1) * kD);
                     // one dot per lane: frame u = r - W - 1 + hl of the stream's tile (lanes 0 .. NB+1 of the half), or the
                     // window's negated mean
                     const int u = r - W - 1 + hl;
-                    const float* vp = is_a ? Mu + (hl - 12) * kD : Xs + min(max(u, 0), x_rows - 1) * kXS;
-                    float g = dot16(ar, ld_row(vp));
+                    if (!is_a) v = ld_row(Xs + min(max(u, 0), x_rows - 1) * kXS);   // (the A lanes keep their mean: a mean row
+                    float g = dot16(ar, v);                                          // read beside seven frame rows conflicts)
                     if (!is_a && u < 0) g = 0.f;
                     // the DP lanes fetch A (negated mean: A = -dot) and their ten G values from their own half
                     const float A = -__shfl_sync(0xffffffffu, g, hbase + 12 + wj);
@@ -245,7 +255,7 @@ cudaError_t launch_dtw_windows_cadence(const DtwWindowsArgs& a, const float* tmp
     const int n_warps = a.n_slots < kMaxWarps ? a.n_slots : kMaxWarps;
     const int x_rows = NWIN + a.max_len + W + 1;
     const int inv_cols = a.max_len + W + 1;
-    const size_t bytes = ((size_t)2 * x_rows * kXS + (size_t)n_warps * 2 * NWIN * kD + (size_t)n_warps * 2 * NWIN * inv_cols) * sizeof(float);
+    const size_t bytes = ((size_t)2 * x_tile_floats(x_rows) + (size_t)n_warps * 2 * NWIN * kD + (size_t)n_warps * 2 * NWIN * inv_cols) * sizeof(float);
     if (bytes > 200 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(dtw_windows_cadence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;

@@ -20,7 +20,11 @@ for i, r in enumerate(rpws):
     bt.add_wakeword_from_buffer(f"w{i}", r)
 bt.set_cuda_stream(torch.cuda.current_stream().cuda_stream)
 nd = 0
+dtw = []
 for k in range(calls):
     nd += bt.process_count(audio[:, 480 * k: 480 * (k + 1)].contiguous())
+    if k >= 40:
+        dtw.append(bt.last_timings()["dtw_ms"])
 torch.cuda.synchronize()
-print("detections", nd, "windows", bt.windows_scored(), "stage", bt.last_timings())
+dtw.sort()
+print("detections", nd, "windows", bt.windows_scored(), "dtw_ms median", round(dtw[len(dtw) // 2], 4) if dtw else None, "stage", bt.last_timings())
