@@ -9,7 +9,7 @@ sys.path.insert(0, ".")
 import rustpotter_b200 as rp  # noqa: E402
 
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
-variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 5, 3]
+variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
 g = torch.Generator(device="cuda").manual_seed(1234)
 scale = torch.tensor([8, 4, 3, 2, 2, 1.5] + [1.0] * 10, device="cuda")
 a = torch.randn((P, 120, 16), device="cuda", generator=g) * scale
