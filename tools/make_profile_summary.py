@@ -86,11 +86,41 @@ def text(name):
     return open(path).read().rstrip() if os.path.exists(path) else None
 
 
+NARRATIVE = """## What the round's numbers say
+
+- **Headline (BASELINE config 5, 65 536 streams x 4 WakewordRefs, Median, strong-scaled)**: 47.3 M windows/s resident and
+  46.6 M end to end (f32 from pinned host, H2D and the D2H of the detections in the timed region) on one B200; 94.6 M on two,
+  378.6 M on eight (8.00x). End to end at N=8: 349 M from i16, 259 M from f32 -- eight GPUs pulling 42 GB of f32 per 155 ms step
+  reach the host's ~190 GB/s. The reference algorithm (C++ oracle, 16 host threads) on the same inputs: 15.2-15.6 k windows/s;
+  the GPU detections of the CPU sample match it to 1.0e-7 relative in the run.
+- **K2p (window scorer, 92 % of the step)** went from 1347 to 1143 ms per step in the second half of the round: role loops
+  without divergence bookkeeping, uniform-datapath template rows, shared-space addresses in registers, MUFU.RSQ without the
+  denormal rescue, two rows per barrier (164 -> 110 instructions per template row and window). It is now bound by the
+  shared-memory pipe (70 % of its wavefront peak) and barrier/dependency latency, not by issue slots; 4 / 5 / 6 CTAs per SM
+  measure the same.
+- **K2s (config 4, the `roofline` object)**: 6.5 ms per 1 M pairs = 0.33 of the measured 6.547 TB/s. Not traffic-bound (14.90 GB
+  moved for 14.08 GB algorithmic). `r02_k2s_ceiling2.txt` takes the kernel apart: step body alone 0.85, + exchange 0.76, +
+  masks 0.73, + producer barrier protocol 0.68, + producer stores 0.61, + their arithmetic 0.58, + their loads 0.56 = the
+  kernel's steady state; `r02_k2s_phases.txt` shows the rest (84-step dependency chain per group with 292 of 336 warp-steps
+  useful, prologue 5.7 %, barrier waits 9 % on the critical warp). Two rebuilt variants (bulk-copy loaders v5, raw rows + consumer
+  norms v6) measured slower. The 0.70 target is not reached and not reachable with FP32 CUDA cores on this mapping.
+- **K2c (30 ms cadence)**: 7.27 ms (K2p's tile mapping) -> 1.77 ms per call of 4096 streams x 36 templates; the before/after
+  captures show the bank conflicts (102.7 M -> 6.0 M) that the last change removed.
+- **K1**: 10 M frames in 13.2 ms (754 M frames/s, 531 GB/s algorithmic, issue/shared-memory bound); max |error| vs the oracle
+  3.7e-5 at mfcc_size 16 (`r02_k1_error.json`).
+- **Tools**: memcheck, racecheck and synccheck are clean over the GPU suite (logs below). racecheck found one benign hazard
+  (a value read and ignored) in K2s and intra-warp hazards in the retired v3 kernel; synccheck rejected an aligned `bar.sync`
+  reached from different program locations in K2p's role loops (now `barrier.sync`).
+
+"""
+
+
 def main():
     o = sys.stdout
     o.write("# Round 2 profile summary (B200, sm_100a)\n\n")
     o.write("Everything below is copied from files in this directory; regenerate with `python tools/make_profile_summary.py`. "
             "ncu ran with `--clock-control none`; numbers printed under ncu are never bench values.\n\n")
+    o.write(NARRATIVE)
     o.write("## Bench lines (`bench.py`, CUDA-event timing, max over ranks)\n\n")
     o.write("| file | workload | N | value (resident) | e2e f32 | e2e i16 | ms/step | roofline K2s | cpu_baseline |\n|---|---|---|---|---|---|---|---|---|\n")
     for f in sorted(os.listdir(P)):
