@@ -453,3 +453,46 @@ def test_bench_reference_arm_prints_the_contract_line():
     cb = j["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == j["value"] and "sample" in cb
     assert "configs[4]" in j["config"]["workload"]
+
+
+def test_rpw_reader_survives_mutated_files():
+    """Untrusted input across the C ABI: a few thousand corruptions of real .rpw files (byte flips, header rewrites,
+    truncations, splices, length fields blown up) either parse or fail with a format error -- never crash, hang or report
+    shapes the buffer cannot hold."""
+    L = rp.lib()
+    info = api.WakewordInfo()
+    rng = np.random.default_rng(20261017)
+    seeds = [open(golden(n), "rb").read() for n in ("alexa.rpw", "oye_casa_g.rpw", "oye_casa_g_v2.rpw")]
+    ok = bad = 0
+    for it in range(3000):
+        src = bytearray(seeds[it % len(seeds)])
+        kind = it % 5
+        if kind == 0:       # a handful of random byte flips, biased to the head (map header, keys, array headers)
+            for _ in range(int(rng.integers(1, 6))):
+                pos = int(rng.integers(0, min(len(src), 4096 if rng.random() < 0.7 else len(src))))
+                src[pos] = int(rng.integers(0, 256))
+        elif kind == 1:     # truncation
+            src = src[: int(rng.integers(0, len(src)))]
+        elif kind == 2:     # a CBOR length byte turned into a huge 64-bit length
+            pos = int(rng.integers(0, min(len(src), 2048)))
+            src[pos:pos + 1] = bytes([0x9B if rng.random() < 0.5 else 0x5B]) + bytes([0x7F] + [0xFF] * 7)
+        elif kind == 3:     # splice of two files
+            other = seeds[(it + 1) % len(seeds)]
+            cut = int(rng.integers(0, len(src)))
+            src = src[:cut] + other[int(rng.integers(0, len(other))):]
+        else:               # random garbage after a plausible head
+            src = src[: int(rng.integers(1, 64))] + bytes(rng.integers(0, 256, int(rng.integers(0, 512)), dtype=np.uint8))
+        buf = bytes(src)
+        rc = L.rp_wakeword_inspect(buf, len(buf), C.byref(info))
+        if rc == 0:
+            ok += 1
+            assert 0 < info.mfcc_size <= 0xFFFF and 0 <= info.n_templates and 0 <= info.max_frames
+            # what it claims to hold must fit the buffer (f32 rows at the very least 2 bytes per float in CBOR half floats)
+            assert info.n_templates * info.max_frames * info.mfcc_size * 2 <= max(len(buf), 1) * 8 or info.n_templates == 0
+            for t in range(-1, min(info.n_templates, 3)):
+                rows = L.rp_wakeword_template(buf, len(buf), t, None, None, 0)
+                assert rows >= -8
+        else:
+            bad += 1
+            assert rc in (-3, -4, -1), rc      # RP_ERR_FORMAT, RP_ERR_UNSUPPORTED, RP_ERR_INVALID
+    assert bad > 1000 and ok >= 0
